@@ -1,0 +1,484 @@
+// Blocked right-looking LU / Cholesky and the triangular solves behind
+// LAPACKE_?{getrf,getrs,getri,gesv,potrf,potrs,posv} — the routines Jalla reaches at
+// /root/reference/Numeric/Jalla/Matrix.hs:503 (gesv), :766 (getrf), :769 (getri) and binds
+// raw at Foreign/LAPACKE.chs:703-706,733-736,741-744,601-604.
+// Structure (reference-LAPACK's, re-cut for the GPU): a narrow panel is factorised by one
+// CTA that keeps the panel in shared memory, row interchanges are applied by a swap
+// kernel, the block row is solved against the unit-lower diagonal block, and the trailing
+// matrix is updated by this library's own GEMM (gemm_device: DMMA for double).
+#include "jb_common.cuh"
+
+namespace jb {
+
+constexpr int NB = 32;           // panel width of the blocked algorithms
+constexpr int PANEL_THREADS = 1024;
+
+// ------------------------------------------------------------------ LU panel (getf2)
+// Factorises the pm x jb panel P (column-major, ld) in place with partial pivoting.
+// Pivot = first row of maximal |re|+|im| (i?amax semantics, lowest index wins ties).
+// ipiv (1-based, global row numbers = local + row_off) and the first zero pivot
+// (info, 1-based global column) are written to device memory.
+template <typename T>
+__global__ void __launch_bounds__(PANEL_THREADS)
+lu_panel_kernel(int pm, int jb, T *__restrict__ Pg, int ldg, int *__restrict__ ipiv, int *info, int row_off,
+                int use_smem) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using R = typename Num<T>::R;
+  __shared__ R red_val[32];
+  __shared__ int red_idx[32];
+  __shared__ int s_piv;
+  __shared__ T s_row[NB];
+  T *P = Pg;
+  int ld = ldg;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (use_smem) {
+    P = reinterpret_cast<T *>(smem_raw);
+    ld = pm | 1;   // odd leading dimension: row-wise accesses (swaps) spread over banks
+    for (int c = 0; c < jb; c++)
+      for (int r = tid; r < pm; r += nt) P[r + (size_t)c * ld] = Pg[r + (size_t)c * ldg];
+    __syncthreads();
+  }
+  for (int c = 0; c < jb && c < pm; c++) {
+    // --- pivot search over rows c..pm-1 of column c
+    R best = (R)-1;
+    int bi = 0x7fffffff;
+    for (int r = c + tid; r < pm; r += nt) {
+      R v = Num<T>::abs1(P[r + (size_t)c * ld]);
+      if (v > best) { best = v; bi = r; }
+    }
+    // NaNs never win (matches i?amax on OpenBLAS where comparisons with NaN are false)
+    for (int off = 16; off > 0; off >>= 1) {
+      R ov = __shfl_down_sync(0xffffffffu, best, off);
+      int oi = __shfl_down_sync(0xffffffffu, bi, off);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if ((tid & 31) == 0) { red_val[tid >> 5] = best; red_idx[tid >> 5] = bi; }
+    __syncthreads();
+    if (tid < 32) {
+      int nw = (nt + 31) >> 5;
+      best = tid < nw ? red_val[tid] : (R)-1;
+      bi = tid < nw ? red_idx[tid] : 0x7fffffff;
+      for (int off = 16; off > 0; off >>= 1) {
+        R ov = __shfl_down_sync(0xffffffffu, best, off);
+        int oi = __shfl_down_sync(0xffffffffu, bi, off);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+      }
+      if (tid == 0) {
+        if (bi == 0x7fffffff) bi = c;   // column of NaNs: keep the diagonal like i?amax returning 1
+        s_piv = bi;
+        ipiv[c] = bi + row_off + 1;
+      }
+    }
+    __syncthreads();
+    const int p = s_piv;
+    // --- swap rows c and p across the panel, stash the pivot row
+    if (tid < jb) {
+      T a = P[c + (size_t)tid * ld], b = P[p + (size_t)tid * ld];
+      if (p != c) { P[c + (size_t)tid * ld] = b; P[p + (size_t)tid * ld] = a; }
+      s_row[tid] = (p != c) ? b : a;
+    }
+    __syncthreads();
+    const T piv = s_row[c];
+    const bool zero = Num<T>::is_zero(piv);
+    if (zero) {
+      if (tid == 0 && *info == 0) *info = c + row_off + 1;
+    }
+    const T rinv = zero ? Num<T>::zero() : Num<T>::recip(piv);
+    // --- scale the column and rank-1 update of the remaining panel columns
+    for (int r = c + 1 + tid; r < pm; r += nt) {
+      T l = P[r + (size_t)c * ld];
+      if (!zero) { l = Num<T>::cmul(l, rinv); P[r + (size_t)c * ld] = l; }
+      for (int cc = c + 1; cc < jb; cc++)
+        P[r + (size_t)cc * ld] = Num<T>::msub(P[r + (size_t)cc * ld], l, s_row[cc]);
+    }
+    __syncthreads();
+  }
+  if (use_smem) {
+    for (int c = 0; c < jb; c++)
+      for (int r = tid; r < pm; r += nt) Pg[r + (size_t)c * ldg] = P[r + (size_t)c * ld];
+  }
+}
+
+// Applies interchanges ipiv[k0..k1) (1-based global rows) to columns [c0,c1) of A, forward.
+template <typename T>
+__global__ void laswp_kernel(T *__restrict__ A, int lda, int c0, int c1, const int *__restrict__ ipiv, int k0, int k1) {
+  int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= c1) return;
+  T *col = A + (size_t)c * lda;
+  for (int k = k0; k < k1; k++) {
+    int p = ipiv[k] - 1;
+    if (p != k) { T t = col[k]; col[k] = col[p]; col[p] = t; }
+  }
+}
+
+// ------------------------------------------------------------------ small triangular solves
+// Effective triangular block M (jb x jb, jb <= 32) = op(Ablk) with op applied on load.
+// mode bits: 1 = effective-lower (forward), 0 = effective-upper (backward); unit = implicit 1 diagonal.
+template <typename T>
+__device__ inline void load_tri_block(T (*Ms)[NB + 1], const T *__restrict__ Ablk, int lda, int jb, int trans) {
+  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
+    int r = e % NB, c = e / NB;
+    T v = Num<T>::zero();
+    if (r < jb && c < jb) {
+      v = (trans == 111) ? Ablk[r + (size_t)c * lda] : Ablk[c + (size_t)r * lda];
+      if (trans == 113) v = Num<T>::conj(v);
+    }
+    Ms[r][c] = v;
+  }
+}
+
+// Left side: solve M X = B for X (overwrites B: jb x nrhs, column-major).  One warp per
+// right-hand side, lane = row; the solved component is broadcast by shuffle.
+template <typename T>
+__global__ void __launch_bounds__(256)
+trsm_small_left_kernel(int lower, int unit, int trans, int jb, int nrhs, const T *__restrict__ Ablk, int lda,
+                       T *__restrict__ B, int ldb, const int *skip) {
+  if (skip && *skip) return;
+  __shared__ T Ms[NB][NB + 1];
+  load_tri_block<T>(Ms, Ablk, lda, jb, trans);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int c = blockIdx.x * nw + warp; c < nrhs; c += gridDim.x * nw) {
+    T *b = B + (size_t)c * ldb;
+    T x = lane < jb ? b[lane] : Num<T>::zero();
+    if (lower) {
+      for (int i = 0; i < jb; i++) {
+        T xi = x;
+        if (!unit && lane == i) xi = Num<T>::cmul(x, Num<T>::recip(Ms[i][i]));
+        if constexpr (Num<T>::cplx) {
+          xi.x = __shfl_sync(0xffffffffu, xi.x, i); xi.y = __shfl_sync(0xffffffffu, xi.y, i);
+        } else {
+          xi = __shfl_sync(0xffffffffu, xi, i);
+        }
+        if (lane == i) x = xi;
+        else if (lane > i) x = Num<T>::msub(x, Ms[lane][i], xi);
+      }
+    } else {
+      for (int i = jb - 1; i >= 0; i--) {
+        T xi = x;
+        if (!unit && lane == i) xi = Num<T>::cmul(x, Num<T>::recip(Ms[i][i]));
+        if constexpr (Num<T>::cplx) {
+          xi.x = __shfl_sync(0xffffffffu, xi.x, i); xi.y = __shfl_sync(0xffffffffu, xi.y, i);
+        } else {
+          xi = __shfl_sync(0xffffffffu, xi, i);
+        }
+        if (lane == i) x = xi;
+        else if (lane < i) x = Num<T>::msub(x, Ms[lane][i], xi);
+      }
+    }
+    if (lane < jb) b[lane] = x;
+  }
+}
+
+// Right side: solve X M = B for X (B is nrows x jb, column-major), M effective-upper
+// (= op(Ablk)); one thread per row of B, the row lives in registers.
+// Used by Cholesky-lower: L21 <- A21 * L11^{-H}  (M = L11^H, trans = 113).
+template <typename T>
+__global__ void __launch_bounds__(256)
+trsm_small_right_upper_kernel(int trans, int jb, int nrows, const T *__restrict__ Ablk, int lda, T *__restrict__ B,
+                              int ldb, const int *skip) {
+  if (skip && *skip) return;
+  __shared__ T Ms[NB][NB + 1];
+  load_tri_block<T>(Ms, Ablk, lda, jb, trans);
+  __syncthreads();
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nrows) return;
+  T x[NB];
+#pragma unroll
+  for (int c = 0; c < NB; c++) x[c] = c < jb ? B[r + (size_t)c * ldb] : Num<T>::zero();
+#pragma unroll
+  for (int c = 0; c < NB; c++) {
+    if (c < jb) {
+      T s = x[c];
+#pragma unroll
+      for (int p = 0; p < c; p++) s = Num<T>::msub(s, x[p], Ms[p][c]);
+      x[c] = Num<T>::cmul(s, Num<T>::recip(Ms[c][c]));
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NB; c++)
+    if (c < jb) B[r + (size_t)c * ldb] = x[c];
+}
+
+// ------------------------------------------------------------------ Cholesky diagonal block (potf2)
+// One CTA of 32x32 threads... kept simple: 1024 threads, block in shared memory,
+// right-looking; info = first non-positive pivot (1-based global index), block left
+// partially factored like ?potf2.  Only the uplo triangle is read or written.
+template <typename T>
+__global__ void __launch_bounds__(1024)
+potf2_block_kernel(int lower, int jb, T *__restrict__ A, int lda, int *info, int off) {
+  if (*info) return;
+  using R = typename Num<T>::R;
+  __shared__ T S[NB][NB + 1];   // S[r][c], lower-effective: for upper we load the conj transpose
+  __shared__ int s_fail;
+  const int r = threadIdx.x % NB, c = threadIdx.x / NB;
+  if (threadIdx.x == 0) s_fail = 0;
+  T v = Num<T>::zero();
+  if (r < jb && c < jb && r >= c) {
+    v = lower ? A[r + (size_t)c * lda] : Num<T>::conj(A[c + (size_t)r * lda]);
+  }
+  S[r][c] = v;
+  __syncthreads();
+  for (int j = 0; j < jb; j++) {
+    R d = Num<T>::re(S[j][j]);
+    if (!(d > (R)0)) {
+      if (threadIdx.x == 0) { s_fail = j + 1; }
+      __syncthreads();
+      break;
+    }
+    R sq = sqrt(d), rinv = (R)1 / sq;
+    __syncthreads();
+    if (c == j && r == j) S[j][j] = Num<T>::make(sq, 0);
+    if (c == j && r > j && r < jb) S[r][j] = Num<T>::scale(S[r][j], rinv);
+    __syncthreads();
+    if (c > j && r >= c && r < jb) S[r][c] = Num<T>::msub(S[r][c], S[r][j], Num<T>::conj(S[c][j]));
+    __syncthreads();
+  }
+  if (r < jb && c < jb && r >= c) {
+    T o = S[r][c];
+    if (lower) A[r + (size_t)c * lda] = o; else A[c + (size_t)r * lda] = Num<T>::conj(o);
+  }
+  if (threadIdx.x == 0 && s_fail) *info = off + s_fail;
+}
+
+// ------------------------------------------------------------------ helpers for getri / getrs
+template <typename T>
+__global__ void set_identity_kernel(int n, T *W, int ldw) {
+  for (int j = blockIdx.y; j < n; j += gridDim.y)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+      W[(size_t)i + (size_t)j * ldw] = (i == j) ? Num<T>::one() : Num<T>::zero();
+}
+template <typename T>
+__global__ void diag_zero_kernel(int n, const T *A, int lda, int *info) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    if (Num<T>::is_zero(A[(size_t)i + (size_t)i * lda])) atomicMin(info, i + 1);
+}
+// perm[i] = source row that ends up in row i after applying ipiv[0..n) forward to the identity
+__global__ void perm_from_ipiv_kernel(int n, const int *__restrict__ ipiv, int *__restrict__ perm, int use_smem) {
+  // single CTA; the swap chain is inherently sequential (n dependent swaps of ints), so it
+  // runs on one thread against shared memory when the two arrays fit
+  extern __shared__ int sm_perm[];
+  int *w = use_smem ? sm_perm : perm;
+  int *piv = use_smem ? sm_perm + n : nullptr;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { w[i] = i; if (use_smem) piv[i] = ipiv[i]; }
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (int k = 0; k < n; k++) {
+      int p = (use_smem ? piv[k] : ipiv[k]) - 1;
+      if (p != k && p >= 0 && p < n) { int t = w[k]; w[k] = w[p]; w[p] = t; }
+    }
+  __syncthreads();
+  if (use_smem) for (int i = threadIdx.x; i < n; i += blockDim.x) perm[i] = w[i];
+}
+// out[i,:] = in[perm[i],:]  (inverse=0)   or   out[perm[i],:] = in[i,:]  (inverse=1)
+template <typename T>
+__global__ void permute_rows_kernel(int inverse, int n, int nrhs, const int *__restrict__ perm, const T *__restrict__ in,
+                                    int ldi, T *__restrict__ out, int ldo) {
+  for (int j = blockIdx.y; j < nrhs; j += gridDim.y)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+      int p = perm[i];
+      if (inverse) out[(size_t)p + (size_t)j * ldo] = in[(size_t)i + (size_t)j * ldi];
+      else out[(size_t)i + (size_t)j * ldo] = in[(size_t)p + (size_t)j * ldi];
+    }
+}
+
+// ------------------------------------------------------------------ host-side drivers
+template <typename T>
+int getrf_device(int m, int n, T *A, int lda, int *d_ipiv, int *d_info, cudaStream_t s) {
+  const int mn = m < n ? m : n;
+  if (mn <= 0) return 0;
+  const size_t smem_cap = 200 * 1024;
+  JB_CUDA(cudaFuncSetAttribute(lu_panel_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+  for (int j0 = 0; j0 < mn; j0 += NB) {
+    const int jb = (mn - j0 < NB) ? (mn - j0) : NB;
+    const int pm = m - j0;
+    size_t need = (size_t)(pm | 1) * jb * sizeof(T);
+    int use_smem = need <= smem_cap;
+    int threads = pm >= PANEL_THREADS ? PANEL_THREADS : ((pm + 31) / 32) * 32;
+    if (threads < 64) threads = 64;
+    lu_panel_kernel<T><<<1, threads, use_smem ? need : 0, s>>>(pm, jb, A + j0 + (size_t)j0 * lda, lda, d_ipiv + j0, d_info,
+                                                              j0, use_smem);
+    count_launch();
+    // panel ipiv holds global row numbers; interchange the columns left and right of the panel
+    if (j0 > 0) {
+      laswp_kernel<T><<<(j0 + 127) / 128, 128, 0, s>>>(A, lda, 0, j0, d_ipiv, j0, j0 + jb);
+      count_launch();
+    }
+    const int nr = n - j0 - jb;
+    if (nr > 0) {
+      laswp_kernel<T><<<(nr + 127) / 128, 128, 0, s>>>(A, lda, j0 + jb, n, d_ipiv, j0, j0 + jb);
+      count_launch();
+      int blocks = (nr + 7) / 8; if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
+      trsm_small_left_kernel<T><<<blocks, 256, 0, s>>>(1, 1, 111, jb, nr, A + j0 + (size_t)j0 * lda, lda,
+                                                       A + j0 + (size_t)(j0 + jb) * lda, lda, nullptr);
+      count_launch();
+      const int mr = m - j0 - jb;
+      if (mr > 0) {
+        int rc = gemm_device<T>(111, 111, mr, nr, jb, Num<T>::neg(Num<T>::one()), A + (j0 + jb) + (size_t)j0 * lda, lda,
+                                A + j0 + (size_t)(j0 + jb) * lda, lda, Num<T>::one(),
+                                A + (j0 + jb) + (size_t)(j0 + jb) * lda, lda, s, 0);
+        if (rc) return rc;
+      }
+    }
+  }
+  JB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Blocked solve op(Tri) X = B in place; Tri is the n x n triangle stored in A
+// (stored_lower selects which triangle of A holds it; trans applies op).
+template <typename T>
+static int trsm_left_blocked(int stored_lower, int trans, int unit, int n, int nrhs, const T *A, int lda, T *B, int ldb,
+                             cudaStream_t s) {
+  const int eff_lower = (trans == 111) ? stored_lower : !stored_lower;
+  const int nblk = (n + NB - 1) / NB;
+  int blocks = (nrhs + 7) / 8; if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
+  const T minus1 = Num<T>::neg(Num<T>::one()), one = Num<T>::one();
+  for (int bi = 0; bi < nblk; bi++) {
+    const int blk = eff_lower ? bi : (nblk - 1 - bi);
+    const int j0 = blk * NB, jb = (n - j0 < NB) ? (n - j0) : NB;
+    trsm_small_left_kernel<T><<<blocks, 256, 0, s>>>(eff_lower, unit, trans, jb, nrhs, A + j0 + (size_t)j0 * lda, lda,
+                                                     B + j0, ldb, nullptr);
+    count_launch();
+    int rc = 0;
+    if (eff_lower) {
+      const int rem = n - j0 - jb;
+      if (rem > 0) {
+        // B[j0+jb:, :] -= op(A)[j0+jb:, j0:j0+jb] * X
+        const T *Ab = (trans == 111) ? A + (j0 + jb) + (size_t)j0 * lda : A + j0 + (size_t)(j0 + jb) * lda;
+        rc = gemm_device<T>(trans, 111, rem, nrhs, jb, minus1, Ab, lda, B + j0, ldb, one, B + j0 + jb, ldb, s, 0);
+      }
+    } else if (j0 > 0) {
+      // B[0:j0, :] -= op(A)[0:j0, j0:j0+jb] * X
+      const T *Ab = (trans == 111) ? A + (size_t)j0 * lda : A + j0;
+      rc = gemm_device<T>(trans, 111, j0, nrhs, jb, minus1, Ab, lda, B + j0, ldb, one, B, ldb, s, 0);
+    }
+    if (rc) return rc;
+  }
+  JB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <typename T>
+static int apply_row_perm(int inverse, int n, int nrhs, const int *d_ipiv, T *B, int ldb, cudaStream_t s) {
+  int *perm = nullptr;
+  T *W = nullptr;
+  if (int rc = ws_alloc((void **)&perm, sizeof(int) * (size_t)n, s)) return rc;
+  if (int rc = ws_alloc((void **)&W, sizeof(T) * (size_t)n * nrhs, s)) { ws_free(perm, s); return rc; }
+  const int perm_smem = (size_t)n * 2 * sizeof(int) <= 48 * 1024;
+  perm_from_ipiv_kernel<<<1, 256, perm_smem ? (size_t)n * 2 * sizeof(int) : 0, s>>>(n, d_ipiv, perm, perm_smem);
+  dim3 grid((unsigned)min((n + 255) / 256, 1024), (unsigned)min(nrhs, 4096));
+  permute_rows_kernel<T><<<grid, 256, 0, s>>>(inverse, n, nrhs, perm, B, ldb, W, n);
+  count_launch(2);
+  int rc = lacpy_device<T>(111, n, nrhs, W, n, B, ldb, s);
+  ws_free(W, s);
+  ws_free(perm, s);
+  return rc;
+}
+
+template <typename T>
+int getrs_device(char trans, int n, int nrhs, const T *A, int lda, const int *d_ipiv, T *B, int ldb, cudaStream_t s) {
+  if (n <= 0 || nrhs <= 0) return 0;
+  int rc;
+  if (trans == 'N' || trans == 'n') {
+    if ((rc = apply_row_perm<T>(0, n, nrhs, d_ipiv, B, ldb, s))) return rc;
+    if ((rc = trsm_left_blocked<T>(1, 111, 1, n, nrhs, A, lda, B, ldb, s))) return rc;
+    if ((rc = trsm_left_blocked<T>(0, 111, 0, n, nrhs, A, lda, B, ldb, s))) return rc;
+  } else {
+    int t = (trans == 'C' || trans == 'c') ? 113 : 112;
+    if ((rc = trsm_left_blocked<T>(0, t, 0, n, nrhs, A, lda, B, ldb, s))) return rc;   // U^T y = b
+    if ((rc = trsm_left_blocked<T>(1, t, 1, n, nrhs, A, lda, B, ldb, s))) return rc;   // L^T z = y
+    if ((rc = apply_row_perm<T>(1, n, nrhs, d_ipiv, B, ldb, s))) return rc;            // x = P^T z
+  }
+  return 0;
+}
+
+// inv(A) from the LU factors: solves A X = I with the stored factors and overwrites A.
+// (?getri forms inv(U) and solves X L = inv(U); same inverse, different operation order —
+// the parity criterion for this row is the residual bound, see tests/test_lapacke_parity.py.)
+template <typename T>
+int getri_device(int n, T *A, int lda, const int *d_ipiv, int *d_info, cudaStream_t s) {
+  if (n <= 0) return 0;
+  JB_CUDA(cudaMemsetAsync(d_info, 0x7f, sizeof(int), s));   // large sentinel for atomicMin
+  diag_zero_kernel<T><<<(n + 255) / 256, 256, 0, s>>>(n, A, lda, d_info);
+  count_launch();
+  int h = 0;
+  JB_CUDA(cudaMemcpyAsync(&h, d_info, sizeof(int), cudaMemcpyDeviceToHost, s));
+  JB_CUDA(cudaStreamSynchronize(s));
+  if (h != 0x7f7f7f7f) {          // singular: U(i,i) == 0, A left as the LU factors
+    JB_CUDA(cudaMemcpyAsync(d_info, &h, sizeof(int), cudaMemcpyHostToDevice, s));
+    return 0;
+  }
+  JB_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int), s));
+  T *W = nullptr;
+  if (int rc = ws_alloc((void **)&W, sizeof(T) * (size_t)n * n, s)) return rc;
+  dim3 grid((unsigned)min((n + 255) / 256, 1024), (unsigned)min(n, 4096));
+  set_identity_kernel<T><<<grid, 256, 0, s>>>(n, W, n);
+  count_launch();
+  int rc = getrs_device<T>('N', n, n, A, lda, d_ipiv, W, n, s);
+  if (!rc) rc = lacpy_device<T>(111, n, n, W, n, A, lda, s);
+  ws_free(W, s);
+  return rc;
+}
+
+template <typename T>
+int potrf_device(char uplo, int n, T *A, int lda, int *d_info, cudaStream_t s) {
+  if (n <= 0) return 0;
+  const int lower = (uplo == 'L' || uplo == 'l');
+  const T minus1 = Num<T>::neg(Num<T>::one()), one = Num<T>::one();
+  for (int j0 = 0; j0 < n; j0 += NB) {
+    const int jb = (n - j0 < NB) ? (n - j0) : NB;
+    T *Ajj = A + j0 + (size_t)j0 * lda;
+    potf2_block_kernel<T><<<1, 1024, 0, s>>>(lower, jb, Ajj, lda, d_info, j0);
+    count_launch();
+    const int rem = n - j0 - jb;
+    if (rem <= 0) break;
+    int rc;
+    if (lower) {
+      T *A21 = A + (j0 + jb) + (size_t)j0 * lda;
+      trsm_small_right_upper_kernel<T><<<(rem + 255) / 256, 256, 0, s>>>(113, jb, rem, Ajj, lda, A21, lda, d_info);
+      count_launch();
+      rc = gemm_device<T>(111, Num<T>::cplx ? 113 : 112, rem, rem, jb, minus1, A21, lda, A21, lda, one,
+                          A + (j0 + jb) + (size_t)(j0 + jb) * lda, lda, s, 'L');
+    } else {
+      T *A12 = A + j0 + (size_t)(j0 + jb) * lda;
+      int blocks = (rem + 7) / 8; if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
+      // U12 <- U11^{-H} A12 : effective-lower solve with M = U11^H
+      trsm_small_left_kernel<T><<<blocks, 256, 0, s>>>(1, 0, 113, jb, rem, Ajj, lda, A12, lda, d_info);
+      count_launch();
+      rc = gemm_device<T>(Num<T>::cplx ? 113 : 112, 111, rem, rem, jb, minus1, A12, lda, A12, lda, one,
+                          A + (j0 + jb) + (size_t)(j0 + jb) * lda, lda, s, 'U');
+    }
+    if (rc) return rc;
+  }
+  JB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <typename T>
+int potrs_device(char uplo, int n, int nrhs, const T *A, int lda, T *B, int ldb, cudaStream_t s) {
+  if (n <= 0 || nrhs <= 0) return 0;
+  const int lower = (uplo == 'L' || uplo == 'l');
+  int rc;
+  if (lower) {
+    if ((rc = trsm_left_blocked<T>(1, 111, 0, n, nrhs, A, lda, B, ldb, s))) return rc;   // L y = b
+    if ((rc = trsm_left_blocked<T>(1, 113, 0, n, nrhs, A, lda, B, ldb, s))) return rc;   // L^H x = y
+  } else {
+    if ((rc = trsm_left_blocked<T>(0, 113, 0, n, nrhs, A, lda, B, ldb, s))) return rc;   // U^H y = b
+    if ((rc = trsm_left_blocked<T>(0, 111, 0, n, nrhs, A, lda, B, ldb, s))) return rc;   // U x = y
+  }
+  return 0;
+}
+
+#define INST(T)                                                                                        \
+  template int getrf_device<T>(int, int, T *, int, int *, int *, cudaStream_t);                        \
+  template int getrs_device<T>(char, int, int, const T *, int, const int *, T *, int, cudaStream_t);   \
+  template int getri_device<T>(int, T *, int, const int *, int *, cudaStream_t);                       \
+  template int potrf_device<T>(char, int, T *, int, int *, cudaStream_t);                              \
+  template int potrs_device<T>(char, int, int, const T *, int, T *, int, cudaStream_t);
+INST(float)
+INST(double)
+INST(cfloat)
+INST(cdouble)
+
+}  // namespace jb

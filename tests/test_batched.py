@@ -1,0 +1,183 @@
+"""Batched small-system parity (BASELINE.json configs[2]: independent 32x32 Double systems,
+getrf + getrs).  The device kernels follow the oracle's arithmetic contract exactly
+(oracle/oracle_impl.inc: r = 1/pivot, l = a*r, a_ij = fma(-l,u,a_ij)), so LU factors,
+pivots and solutions are compared BIT-EXACTLY for real types — on every system, including
+exact ties — and the full-size run is checked through size-independent properties."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from jalla_b200 import _lib, synth
+from jalla_b200._lib import lib, check
+from tests.util import NP, EPS, fro
+
+pytestmark = pytest.mark.gpu
+
+
+class Dev:
+    def __init__(self, arr):
+        self.arr = np.ascontiguousarray(arr) if arr.ndim == 1 else arr
+        self.ptr = lib.jb_malloc(max(self.arr.nbytes, 16), _lib.JB_MEM_DEVICE)
+        assert self.ptr
+        if self.arr.nbytes:
+            check(lib.jb_memcpy_h2d(self.ptr, self.arr.ctypes.data, self.arr.nbytes), "h2d")
+
+    def get(self):
+        check(lib.jb_memcpy_d2h(self.arr.ctypes.data, self.ptr, self.arr.nbytes), "d2h")
+        return self.arr
+
+    def __del__(self):
+        lib.jb_free(self.ptr)
+
+
+def batch_rand(rng, t, batch, n, cols=None, lo=-1.0, hi=1.0):
+    cols = n if cols is None else cols
+    a = rng.uniform(lo, hi, (batch, cols, n))
+    if t in "cz":
+        a = a + 1j * rng.uniform(lo, hi, (batch, cols, n))
+    return a.astype(NP[t])   # [batch][col][row]: column-major matrices, contiguous stride n*cols
+
+
+def oracle_gesv_batch(orc, t, A, b):
+    batch, n = A.shape[0], A.shape[2]
+    LU, X = A.copy(), b.copy()
+    piv = np.zeros((batch, n), np.int32); info = np.zeros(batch, np.int32)
+    for i in range(batch):
+        info[i] = orc.gesv(t, 102, n, b.shape[1], LU[i], n, piv[i], X[i], n)
+    return LU, piv, X, info
+
+
+@pytest.mark.parametrize("t", "sdcz")
+@pytest.mark.parametrize("n", [32, 1, 5, 17, 31])
+def test_gesv_batched_bit_exact(orc, rng, t, n):
+    lib.jb_init(-1)
+    batch = 301
+    A = batch_rand(rng, t, batch, n); b = batch_rand(rng, t, batch, n, 1)
+    if t in "sd":   # exact ties: integer matrices exercise the lowest-index tie-break
+        A[:40] = rng.integers(-2, 3, A[:40].shape).astype(NP[t])
+    LUo, pivo, Xo, infoo = oracle_gesv_batch(orc, t, A, b)
+    dA, dB = Dev(A.copy()), Dev(b.copy())
+    dP, dI = Dev(np.zeros((batch, n), np.int32)), Dev(np.full(batch, -7, np.int32))
+    rc = getattr(lib, f"jb_{t}gesv_batched")(n, 1, dA.ptr, n, n * n, dP.ptr, dB.ptr, n, n, dI.ptr, batch)
+    check(rc, "gesv_batched"); check(lib.jb_sync(), "sync")
+    LU, piv, X, info = dA.get(), dP.get(), dB.get(), dI.get()
+    np.testing.assert_array_equal(info, infoo)
+    np.testing.assert_array_equal(piv, pivo)
+    ok = infoo == 0
+    if t in "sd":
+        np.testing.assert_array_equal(LU, LUo)
+        np.testing.assert_array_equal(X[ok], Xo[ok])
+    else:
+        np.testing.assert_array_equal(LU.view(NP["s" if t == "c" else "d"]), LUo.view(NP["s" if t == "c" else "d"]))
+        np.testing.assert_array_equal(X[ok], Xo[ok])
+    np.testing.assert_array_equal(X[~ok], b[~ok])      # singular systems: B untouched, like ?gesv
+
+
+@pytest.mark.parametrize("t", "sd")
+def test_getrf_getrs_batched_multi_rhs(orc, rng, t):
+    lib.jb_init(-1)
+    batch, n, nrhs = 77, 32, 3
+    A = batch_rand(rng, t, batch, n); B = batch_rand(rng, t, batch, n, nrhs)
+    dA, dB = Dev(A.copy()), Dev(B.copy())
+    dP, dI = Dev(np.zeros((batch, n), np.int32)), Dev(np.zeros(batch, np.int32))
+    check(getattr(lib, f"jb_{t}getrf_batched")(n, dA.ptr, n, n * n, dP.ptr, dI.ptr, batch), "getrf_batched")
+    check(getattr(lib, f"jb_{t}getrs_batched")(n, nrhs, dA.ptr, n, n * n, dP.ptr, dB.ptr, n, n * nrhs, batch), "getrs_batched")
+    check(lib.jb_sync(), "sync")
+    LUo, pivo, Xo, infoo = oracle_gesv_batch(orc, t, A, B)
+    np.testing.assert_array_equal(dP.get(), pivo)
+    np.testing.assert_array_equal(dA.get(), LUo)
+    np.testing.assert_array_equal(dB.get(), Xo)
+    # gesv_batched with nrhs > 1 routes through the same two kernels
+    dA2, dB2 = Dev(A.copy()), Dev(B.copy())
+    check(getattr(lib, f"jb_{t}gesv_batched")(n, nrhs, dA2.ptr, n, n * n, dP.ptr, dB2.ptr, n, n * nrhs, dI.ptr, batch), "gesv_batched")
+    check(lib.jb_sync(), "sync")
+    np.testing.assert_array_equal(dB2.get(), Xo)
+
+
+def test_dsolve_batched_solve_only_contract(orc, rng):
+    """The contract solveLinearSystem exposes (Matrix.hs:513-521): A and B are inputs, only X is produced."""
+    lib.jb_init(-1)
+    batch, n = 500, 32
+    A = batch_rand(rng, "d", batch, n); b = batch_rand(rng, "d", batch, n, 1)
+    dA, dB, dX, dI = Dev(A.copy()), Dev(b.copy()), Dev(np.zeros_like(b)), Dev(np.zeros(batch, np.int32))
+    check(lib.jb_dsolve_batched(n, 1, dA.ptr, n, n * n, dB.ptr, n, n, dX.ptr, n, n, dI.ptr, batch), "dsolve_batched")
+    check(lib.jb_sync(), "sync")
+    _, _, Xo, infoo = oracle_gesv_batch(orc, "d", A, b)
+    np.testing.assert_array_equal(dX.get(), Xo)
+    np.testing.assert_array_equal(dA.get(), A)        # inputs untouched
+    np.testing.assert_array_equal(dB.get(), b)
+
+
+@pytest.mark.parametrize("t", "sdcz")
+@pytest.mark.parametrize("uplo", ["L", "U"])
+@pytest.mark.parametrize("n", [32, 9])
+def test_potrf_potrs_batched(orc, rng, t, uplo, n):
+    lib.jb_init(-1)
+    batch, nrhs = 64, 2
+    M = batch_rand(rng, t, batch, n)
+    S = np.stack([(m.T @ m.T.conj().T + n * np.eye(n)).T for m in M]).astype(NP[t])   # [b][col][row]
+    S[5, 3, 3] = -1.0                                    # one system that is not positive definite
+    B = batch_rand(rng, t, batch, n, nrhs)
+    dS, dB, dI = Dev(S.copy()), Dev(B.copy()), Dev(np.zeros(batch, np.int32))
+    check(getattr(lib, f"jb_{t}potrf_batched")(uplo.encode(), n, dS.ptr, n, n * n, dI.ptr, batch), "potrf_batched")
+    check(getattr(lib, f"jb_{t}potrs_batched")(uplo.encode(), n, nrhs, dS.ptr, n, n * n, dB.ptr, n, n * nrhs, batch), "potrs_batched")
+    check(lib.jb_sync(), "sync")
+    F, X, info = dS.get(), dB.get(), dI.get()
+    for i in range(batch):
+        So, Bo = S[i].copy(), B[i].copy()
+        io = orc.potrf(t, 102, uplo, n, So, n)
+        assert info[i] == io
+        if io:
+            continue
+        orc.potrs(t, 102, uplo, n, nrhs, So, n, Bo, n)
+        tri = np.triu_indices(n) if uplo == "L" else np.tril_indices(n)   # [col][row] storage: transposed view
+        if t in "sd":
+            np.testing.assert_array_equal(F[i][tri], So[tri])
+        else:
+            assert fro(F[i][tri] - So[tri]) <= 50 * n * EPS[t] * fro(So[tri])
+        assert fro(X[i] - Bo) <= 1e3 * n * EPS[t] * fro(Bo)
+
+
+def test_config3_full_size_properties():
+    """configs[2] at full size: 1,000,000 independent 32x32 Double systems from the synthetic
+    generator.  Size-independent checks: every info is 0, every ipiv entry is in [k, n],
+    the batch residual |A x - b| is at the n*eps level, and the first 2000 systems equal a
+    standalone run on that prefix bit for bit (each system independent of its neighbours)."""
+    lib.jb_init(-1)
+    n, batch = 32, 1_000_000
+    dA = lib.jb_malloc(batch * n * n * 8, 0); dB = lib.jb_malloc(batch * n * 8, 0)
+    dP = lib.jb_malloc(batch * n * 4, 0); dI = lib.jb_malloc(batch * 4, 0)
+    assert dA and dB and dP and dI
+    try:
+        # the whole batch is one (n) x (batch*n) column-major matrix of U(-1,1)
+        check(lib.jb_dfill_uniform(dA, n, n, batch * n, 0, 0, 20261019, 0, 0.0), "fill A")
+        check(lib.jb_dfill_uniform(dB, n, n, batch, 0, 0, 20261020, 0, 0.0), "fill b")
+        check(lib.jb_dgesv_batched(n, 1, dA, n, n * n, dP, dB, n, n, dI, batch), "gesv_batched")
+        check(lib.jb_sync(), "sync")
+        info = np.empty(batch, np.int32); piv = np.empty((batch, n), np.int32)
+        check(lib.jb_memcpy_d2h(info.ctypes.data, dI, info.nbytes), "d2h")
+        check(lib.jb_memcpy_d2h(piv.ctypes.data, dP, piv.nbytes), "d2h")
+        assert (info == 0).all()
+        assert (piv >= np.arange(1, n + 1)[None, :]).all() and (piv <= n).all()
+        X = np.empty((batch, n)); check(lib.jb_memcpy_d2h(X.ctypes.data, dB, X.nbytes), "d2h")
+        sel = np.r_[0:2000, batch - 2000:batch]
+        worst = 0.0
+        for i in sel:
+            A = synth.uniform(n, n, 20261019, "d", 0, i * n)
+            b = synth.uniform(n, 1, 20261020, "d", 0, i)[:, 0]
+            r = np.linalg.norm(A @ X[i] - b) / (np.linalg.norm(A) * np.linalg.norm(X[i]) * n * EPS["d"])
+            worst = max(worst, r)
+        assert worst <= 10, worst
+        # prefix run
+        m = 2000
+        A0 = synth.uniform(n, m * n, 20261019, "d"); b0 = synth.uniform(n, m, 20261020, "d")
+        dA0, dB0 = Dev(np.ascontiguousarray(A0.T)), Dev(np.ascontiguousarray(b0.T))
+        dP0, dI0 = Dev(np.zeros((m, n), np.int32)), Dev(np.zeros(m, np.int32))
+        check(lib.jb_dgesv_batched(n, 1, dA0.ptr, n, n * n, dP0.ptr, dB0.ptr, n, n, dI0.ptr, m), "gesv prefix")
+        check(lib.jb_sync(), "sync")
+        np.testing.assert_array_equal(dB0.get(), X[:m])
+        np.testing.assert_array_equal(dP0.get(), piv[:m])
+    finally:
+        for p in (dA, dB, dP, dI):
+            lib.jb_free(p)
