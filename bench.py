@@ -1,0 +1,327 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark of the jalla_b200 hot path (contract: see DESIGN.md §Measurement).
+
+Metric (BASELINE.json): FP64 GEMM TFLOP/s at N=16384 (+ batched 32x32 LU solves/s), each
+as a fraction of roofline, at 1/2/4/8 B200.  One "step" = one pass of the hot path over
+one batch of synthetic input:
+  * primary   — configs[1]: C = A*B, Double, N=16384, NN, alpha=1, beta=0, column-major
+                 (at N>1 the SAME product, 2D-sharded Pr x Pc: strong scaling);
+  * secondary — configs[2]: 1,000,000 independent 32x32 Double systems, getrf+getrs
+                 (batch split across ranks, no collective), reported under "batched_lu".
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+N>1 is launched by torchrun (one rank per GPU).  `--impl reference` times the reference's
+own CPU path — the C boundary Jalla calls, resolved in the OpenBLAS this image ships — on
+the host cores (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_GEMM = 16384
+LU_N, LU_BATCH = 32, 1_000_000
+LU_BYTES_PER_SYSTEM = 17024          # A in 8192 + b in 256 + LU out 8192 + ipiv out 128 + x out 256
+SEED = 20261019
+DMMA_PEAK_TFLOPS = 37.07             # measured: tools/peaks.cu on this pool's B200 (profiles/peaks_r1.jsonl)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d.get("hbm_gbs", 6650.0)), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+    def summary(self, t0, t1):
+        sm, mx, reasons, pw = [], [], set(), []
+        for ts, line in self.rows:
+            if not (t0 <= ts <= t1 + 0.15):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(pw)}
+
+
+# ------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """Jalla's CPU path at the C boundary it calls (cblas_dgemm / LAPACKE_dgetrf+dgetrs), all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import numpy as np
+    from oracle import cpu_ref
+    ob = cpu_ref.openblas()
+    cores = os.cpu_count() or 1
+    cpu_ref.openblas_set_threads(cores)
+    n = 8192                                  # bounded sample of the N=16384 workload (1/8 of its flops)
+    from jalla_b200 import synth
+    A = synth.uniform(n, n, SEED, "d"); B = synth.uniform(n, n, SEED + 1, "d")
+    Cm = np.empty((n, n), order="F")
+    flop = 2.0 * n ** 3
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        ob.gemm("d", 102, 111, 111, n, n, n, 1.0, A, n, B, n, 0.0, Cm, n)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    val = flop / (ms * 1e-3) / 1e12
+    lu = cpu_batched_lu(ob, sample=200000, threads=cores)
+    sample = f"cblas_dgemm N={n} (1/8 of the N=16384 step's flops) per step, OpenBLAS {ob.info.get('core')} x{cores} threads"
+    line = {
+        "impl": "reference", "metric": "dgemm_fp64_n16384_tflops", "value": val, "unit": "TFLOP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[1]: FP64 dgemm N=16384 square (CPU arm runs a bounded N=8192 sample per step)",
+                   "trans": "NN", "alpha": 1, "beta": 0, "layout": "column-major"},
+        "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": cores, "kind": "reference", "sample": sample,
+                         "blas": ob.info.get("config")},
+        "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "batched_lu": lu, "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def cpu_batched_lu(ob, sample, threads):
+    """LAPACKE_dgetrf + LAPACKE_dgetrs per 32x32 system, OpenBLAS single-threaded per call and the
+    batch loop split over host threads (ctypes releases the GIL)."""
+    import numpy as np
+    from oracle import cpu_ref
+    from jalla_b200 import synth
+    n = LU_N
+    A = np.ascontiguousarray(synth.uniform(n, sample * n, SEED, "d").T).reshape(sample, n, n)
+    b = np.ascontiguousarray(synth.uniform(n, sample, SEED + 1, "d").T)
+    piv = np.zeros((sample, n), np.int32)
+    cpu_ref.openblas_set_threads(1)
+    ob.getrf("d", 102, n, n, A[0].copy(), n, piv[0].copy()); ob.getrs("d", 102, "N", n, 1, A[0].copy(), n, piv[0], b[0].copy(), n)
+    f_getrf = ob._cache[("getrf", "d")]; f_getrs = ob._cache[("getrs", "d")]
+    drv = cpu_ref.oracle().lib.oracle_run_batched_lu_procs   # fork-parallel C loop (oracle/cpu_batch_driver.c)
+    drv.restype = C.c_int
+    drv.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int]
+    t0 = time.perf_counter()
+    bad = drv(C.cast(f_getrf, C.c_void_p), C.cast(f_getrs, C.c_void_p), n, A.ctypes.data, piv.ctypes.data, b.ctypes.data, sample, threads)
+    dt = time.perf_counter() - t0
+    assert bad == 0
+    cpu_ref.openblas_set_threads(threads)
+    return {"metric": "batched_lu_32x32_solves_per_s", "value": sample / dt, "unit": "solves/s", "cores": threads,
+            "sample": f"{sample} of the 1,000,000 systems, LAPACKE_dgetrf+dgetrs per system, C loop split over forked processes (one per core), OpenBLAS threads=1"}
+
+
+# ------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="jalla_b200")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--only", default="", help="gemm|lu: restrict the timed work (profiling aid)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    from jalla_b200 import _lib
+    from jalla_b200._lib import lib, check, check_last
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: jalla_b200 has no CPU path"}))
+        return 1
+    torch.cuda.set_device(local_rank)
+    check(lib.jb_init(local_rank), "jb_init")
+    stream = torch.cuda.current_stream()
+    lib.jb_set_stream(C.c_void_p(stream.cuda_stream))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from jalla_b200 import dist as jdist
+    grid = jdist.ProcessGrid(world, rank, dist)
+
+    # ---------------------------------------------------------------- primary: dgemm N=16384
+    N = N_GEMM
+    gemm = jdist.ShardedGemm(grid, N, seed=SEED)       # owns this rank's blocks of A, B, C (device resident)
+    flop = 2.0 * N ** 3
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = lib.jb_kernel_launches()
+    res = {}
+    if args.only in ("", "gemm"):
+        for _ in range(args.warmup):
+            gemm.step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.jb_kernel_launches()
+        t_wall0 = time.time()
+        e0.record(stream)
+        for _ in range(args.steps):
+            gemm.step()
+        e1.record(stream)
+        barrier()
+        t_wall1 = time.time()
+        ms = e0.elapsed_time(e1) / max(args.steps, 1)
+        gemm_launches = lib.jb_kernel_launches() - l0
+        kern_ms = gemm.kernel_ms(reps=3)                 # the local GEMM kernel alone, CUDA events
+        if dist is not None:
+            tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms = float(tms.item())
+        res["gemm"] = (ms, gemm_launches, kern_ms, t_wall0, t_wall1)
+        gemm.verify_sample()
+    # ---------------------------------------------------------------- secondary: batched LU
+    lu = None
+    if args.only in ("", "lu"):
+        lu = jdist.ShardedBatchedLU(grid, LU_N, LU_BATCH, seed=SEED)
+        for _ in range(max(args.warmup, 1)):
+            lu.step()
+        barrier()
+        # the factorisation overwrites its input: each step restores A,b (untimed) and brackets only the
+        # solve kernel with CUDA events on the launching stream; value = batch / mean kernel time, max over ranks
+        lu_kern_ms = lu.kernel_ms(reps=max(args.steps, 1))
+        lu_ms = lu_kern_ms
+        if dist is not None:
+            tms = torch.tensor([lu_ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            lu_ms = float(tms.item())
+        res["lu"] = (lu_ms, lu_kern_ms)
+    total_launches = lib.jb_kernel_launches() - launches0
+    sampler.stop()
+
+    hbm_peak, hbm_src = measured_peaks()
+    out = {}
+    if "gemm" in res:
+        ms, gemm_launches, kern_ms, tw0, tw1 = res["gemm"]
+        value = flop / (ms * 1e-3) / 1e12
+        local_flop = flop / world
+        ach = local_flop / (kern_ms * 1e-3) / 1e12
+        out.update({
+            "metric": "dgemm_fp64_n16384_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[1]: FP64 dgemm N=16384 square, C=A*B (NN, alpha=1, beta=0), column-major ld=rows",
+                       "n": N, "grid": f"{grid.pr}x{grid.pc}", "l2": "operands 2 GiB each >> 126 MB L2, no flush needed",
+                       "inputs": "counter-based U(-1,1) keyed on global (i,j), generated on device"},
+            "roofline": {"bound": "tensor", "achieved": ach, "peak": DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
+                         "frac": ach / DMMA_PEAK_TFLOPS, "traffic": None,
+                         "peak_source": "measured FP64 DMMA issue-rate peak (tools/peaks.cu, profiles/peaks_r1.jsonl); "
+                                        "MEASURED_PEAKS.json holds no FP64 figure",
+                         "kernel": "dgemm_dmma_kernel", "kernel_ms": kern_ms,
+                         "algorithmic_flops_per_launch": local_flop},
+            "gpu_launches": int(total_launches),
+            "clocks": sampler.summary(tw0, tw1),
+        })
+    if "lu" in res:
+        lu_ms, lu_kern_ms = res["lu"]
+        per_rank = lu.local_batch
+        ach = per_rank * LU_BYTES_PER_SYSTEM / (lu_kern_ms * 1e-3) / 1e9
+        out["batched_lu"] = {
+            "metric": "batched_lu_32x32_solves_per_s", "value": LU_BATCH / (lu_ms * 1e-3), "unit": "solves/s",
+            "ms_per_step": lu_ms, "scaling": "strong", "dtype": "f64",
+            "config": {"workload": "configs[2]: 1,000,000 independent 32x32 Double systems, getrf+getrs (jb_dgesv_batched), "
+                                   "batch split across ranks, no collective", "flush": "8.4 GB working set >> L2"},
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                         "traffic": None, "peak_source": hbm_src, "kernel": "lu32_kernel<double,1,true>",
+                         "kernel_ms": lu_kern_ms, "algorithmic_bytes_per_launch": per_rank * LU_BYTES_PER_SYSTEM,
+                         "frac_of_nominal_8TBs": ach / 8000.0},
+        }
+        if "gemm" not in res:
+            out.update({"metric": "batched_lu_32x32_solves_per_s", "value": out["batched_lu"]["value"], "unit": "solves/s",
+                        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": lu_ms,
+                        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                        "config": out["batched_lu"]["config"], "roofline": out["batched_lu"]["roofline"],
+                        "gpu_launches": int(total_launches)})
+    # ---------------------------------------------------------------- e2e through the C ABI with host buffers
+    if "gemm" in res and not args.no_e2e:
+        out["e2e"] = gemm.e2e(steps=min(args.steps, 2))
+    # ---------------------------------------------------------------- CPU baseline (rank 0, N=1 only)
+    if world == 1 and not args.no_cpu and "gemm" in res:
+        from oracle import cpu_ref
+        ob = cpu_ref.openblas()
+        cores = os.cpu_count() or 1
+        cpu_ref.openblas_set_threads(cores)
+        from jalla_b200 import synth
+        n = 8192
+        A = synth.uniform(n, n, SEED, "d"); B = synth.uniform(n, n, SEED + 1, "d"); Cm = np.empty((n, n), order="F")
+        ob.gemm("d", 102, 111, 111, 1024, 1024, 1024, 1.0, A, n, B, n, 0.0, Cm, n)
+        t0 = time.perf_counter()
+        ob.gemm("d", 102, 111, 111, n, n, n, 1.0, A, n, B, n, 0.0, Cm, n)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {
+            "value": 2.0 * n ** 3 / dt / 1e12, "unit": "TFLOP/s", "cores": cores, "kind": "reference",
+            "sample": f"one cblas_dgemm N={n} (1/8 of the step's flops) through the C boundary Jalla calls, "
+                      f"OpenBLAS {ob.info.get('core')} {cores} threads", "blas": ob.info.get("config"),
+            "batched_lu": cpu_batched_lu(ob, sample=200000, threads=cores)}
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
