@@ -73,6 +73,30 @@ def gemm_plan(n: int, pr: int, pc: int, row: int, col: int):
             "gemms": gemms}
 
 
+def summa_step(plan, grid: ProcessGrid, a_blocks, b_blocks, local_gemm):
+    """One distributed product: post every panel broadcast (A panels along the process row, B panels along
+    the process column, all asynchronous), then run the local GEMMs in K order, each waiting only for the
+    panels it consumes.  Backend agnostic (NCCL on GPUs; gloo in the CPU tests): `a_blocks[q]` / `b_blocks[p]`
+    are the tensors panels land in (the owner's slot already holds its data), `local_gemm(g)` runs one
+    entry of plan["gemms"]."""
+    dist = grid.dist
+    a_work, b_work = {}, {}
+    for q, src in plan["a_bcasts"]:
+        a_work[q] = dist.broadcast(a_blocks[q], src=src, group=grid.row_group, async_op=True) if grid.pc > 1 else None
+    for p, src in plan["b_bcasts"]:
+        b_work[p] = dist.broadcast(b_blocks[p], src=src, group=grid.col_group, async_op=True) if grid.pr > 1 else None
+    for g in plan["gemms"]:
+        for q in g["a_panels"]:
+            if a_work.get(q) is not None:
+                a_work[q].wait(); a_work[q] = None
+        if b_work.get(g["p"]) is not None:
+            b_work[g["p"]].wait(); b_work[g["p"]] = None
+        local_gemm(g)
+    for w in list(a_work.values()) + list(b_work.values()):
+        if w is not None:
+            w.wait()
+
+
 class ShardedGemm:
     """configs[1]: one FP64 N x N x N product, 2-D sharded; a step = broadcasts + local GEMMs."""
 
@@ -107,23 +131,8 @@ class ShardedGemm:
         if grid.world == 1:
             self._local_gemm(P["gemms"][0])
             return
-        dist = grid.dist
-        a_work, b_work = {}, {}
-        for q, src in P["a_bcasts"]:
-            blk = self.A_row[q * P["kc"] * P["mb"]:(q + 1) * P["kc"] * P["mb"]]
-            a_work[q] = dist.broadcast(blk, src=src, group=grid.row_group, async_op=True) if grid.pc > 1 else None
-        for p, src in P["b_bcasts"]:
-            b_work[p] = dist.broadcast(self.B_blk[p], src=src, group=grid.col_group, async_op=True) if grid.pr > 1 else None
-        for g in P["gemms"]:
-            for q in g["a_panels"]:
-                if a_work.get(q) is not None:
-                    a_work[q].wait(); a_work[q] = None
-            if b_work.get(g["p"]) is not None:
-                b_work[g["p"]].wait()
-            self._local_gemm(g)
-        for w in a_work.values():
-            if w is not None:
-                w.wait()
+        a_blocks = [self.A_row[q * P["kc"] * P["mb"]:(q + 1) * P["kc"] * P["mb"]] for q in range(grid.pc)]
+        summa_step(P, grid, a_blocks, self.B_blk, self._local_gemm)
 
     def kernel_ms(self, reps=3) -> float:
         """Average duration of this rank's local GEMM work (all K panels) with CUDA events, no collectives."""

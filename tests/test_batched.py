@@ -181,3 +181,18 @@ def test_config3_full_size_properties():
     finally:
         for p in (dA, dB, dP, dI):
             lib.jb_free(p)
+
+
+def test_fast_reciprocal_is_correctly_rounded(rng):
+    """The tuned 32x32 kernel's MUFU.RCP64H + Newton reciprocal must equal IEEE 1/x bit for bit on its
+    guarded exponent range (outside it the kernel falls back to IEEE division)."""
+    lib.jb_init(-1)
+    lib.jb_test_rcp_fast.restype = C.c_longlong
+    lib.jb_test_rcp_fast.argtypes = [C.c_void_p, C.c_int]
+    n = 1 << 22
+    mant = rng.uniform(1.0, 2.0, n)
+    mant[: n // 4] = 1.0 + rng.integers(0, 64, n // 4) * 2.0 ** -52          # just above powers of two
+    mant[n // 4: n // 2] = 2.0 - rng.integers(1, 64, n // 4) * 2.0 ** -52     # significands of all ones
+    x = np.ldexp(mant, rng.integers(-900, 900, n)) * rng.choice([-1.0, 1.0], n)
+    d = Dev(x)
+    assert lib.jb_test_rcp_fast(d.ptr, n) == 0
