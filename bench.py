@@ -285,7 +285,7 @@ def main():
             "config": {"workload": "configs[2]: 1,000,000 independent 32x32 Double systems, getrf+getrs (jb_dgesv_batched), "
                                    "batch split across ranks, no collective", "flush": "8.4 GB working set >> L2"},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                         "traffic": None, "peak_source": hbm_src, "kernel": "lu32_kernel<double,1,true>",
+                         "traffic": None, "peak_source": hbm_src, "kernel": "lu32v2_kernel<1,1,20>",
                          "kernel_ms": lu_kern_ms, "algorithmic_bytes_per_launch": per_rank * LU_BYTES_PER_SYSTEM,
                          "frac_of_nominal_8TBs": ach / 8000.0},
         }
