@@ -33,6 +33,7 @@ LU_N, LU_BATCH = 32, 1_000_000
 LU_BYTES_PER_SYSTEM = 17024          # A in 8192 + b in 256 + LU out 8192 + ipiv out 128 + x out 256
 SEED = 20261019
 DMMA_PEAK_TFLOPS = 37.07             # measured: tools/peaks.cu on this pool's B200 (profiles/peaks_r1.jsonl)
+FFMA_PEAK_TFLOPS = 72.35             # measured: same run (full-precision FP32 FMA, CUDA cores)
 
 
 def measured_peaks():
@@ -168,6 +169,7 @@ def main():
     ap.add_argument("--impl", default="jalla_b200")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-other", action="store_true", help="skip the zgemm / sgemm side measurements")
     ap.add_argument("--only", default="", help="gemm|lu: restrict the timed work (profiling aid)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -295,6 +297,16 @@ def main():
                         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                         "config": out["batched_lu"]["config"], "roofline": out["batched_lu"]["roofline"],
                         "gpu_launches": int(total_launches)})
+    # ---------------------------------------------------------------- configs[4]: zgemm N=8192, sgemm N=16384 (1 GPU)
+    if world == 1 and args.only == "" and not args.no_other:
+        other = {}
+        del lu
+        torch.cuda.empty_cache()
+        for t, n, peak, bound in (("z", 8192, DMMA_PEAK_TFLOPS, "FP64 DMMA"), ("s", 16384, FFMA_PEAK_TFLOPS, "FP32 FFMA (no TF32)")):
+            ms_o, fl = jdist.time_square_gemm(t, n, reps=2)
+            tf = fl / (ms_o * 1e-3) / 1e12
+            other[f"{t}gemm_n{n}"] = {"tflops": tf, "ms": ms_o, "flop": fl, "peak_tflops": peak, "frac": tf / peak, "pipe": bound}
+        out["other_configs"] = other
     # ---------------------------------------------------------------- e2e through the C ABI with host buffers
     if "gemm" in res and not args.no_e2e:
         out["e2e"] = gemm.e2e(steps=min(args.steps, 2))

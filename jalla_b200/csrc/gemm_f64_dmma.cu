@@ -15,7 +15,7 @@
 // operand majors — the permutation is undone for free when C is written.  All four
 // NoTrans/Trans combinations are served without materialising a transpose: an operand is
 // either K-major (one 16x128 box per stage) or MN-major (eight 16x16 boxes per stage).
-#include "jb_common.cuh"
+#include "dmma_common.cuh"
 
 namespace jb {
 namespace dmma {
@@ -28,40 +28,6 @@ constexpr int TILE_BYTES = BM * BK * 8;                 // 16 KiB per operand pe
 constexpr int STAGE_BYTES = 2 * TILE_BYTES;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int GROUP_M = 16;                             // tile rasterisation band (L2 reuse)
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
-}
-__device__ __forceinline__ double lds64(uint32_t addr) {
-  double v;
-  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
 
 // Per-lane fragment geometry.  g = lane>>2 selects the row (A side) / column (B side) of an
 // 8-wide group, t = lane&3 the k index inside a k4 step.
@@ -241,38 +207,9 @@ dgemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 }
 
 // ------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void *p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)p;
-    else
-      cudaGetLastError();
-  }
-  return fn;
-}
-
 // Tensor map of a column-major matrix `rows x cols` (ld) seen as dim0 = rows (contiguous), dim1 = cols.
 static int make_map(CUtensorMap *map, const double *ptr, long rows, long cols, int ld, int box0, int box1) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) { set_error(JB_ERR_CUDA, "cuTensorMapEncodeTiled unavailable"); return JB_ERR_CUDA; }
-  cuuint64_t gdim[2] = {(cuuint64_t)rows, (cuuint64_t)cols};
-  cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(double)};
-  cuuint32_t box[2] = {(cuuint32_t)box0, (cuuint32_t)box1};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(ptr), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error(JB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r); return JB_ERR_CUDA; }
-  return 0;
+  return make_map_f64(map, ptr, rows, cols, (size_t)ld * sizeof(double), box0, box1);
 }
 
 template <bool A_KM, bool B_KM>

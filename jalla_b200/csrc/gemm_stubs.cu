@@ -4,6 +4,4 @@
 namespace jb {
 int sgemm_simt_try(int, int, int, int, int, float, const float *, int, const float *, int, float, float *, int,
                    cudaStream_t, int) { return 0; }
-int zgemm_dmma_try(int, int, int, int, int, cdouble, const cdouble *, int, const cdouble *, int, cdouble, cdouble *, int,
-                   cudaStream_t, int) { return 0; }
 }  // namespace jb

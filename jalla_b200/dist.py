@@ -271,3 +271,37 @@ class ShardedBatchedLU:
             tot += e0.elapsed_time(e1)
         assert int(self.info.abs().max().item()) == 0, "a synthetic system reported info != 0"
         return tot / reps
+
+
+def time_square_gemm(t: str, n: int, reps: int = 2, seed: int = 20261019):
+    """configs[4]-style single-GPU timing of one n x n x n product of element type t ('s','d','c','z'):
+    NN, alpha = 1, beta = 0, inputs from the device generator.  Returns (ms, real flop count)."""
+    import torch
+    from ._lib import lib, check, check_last
+    esz = {"s": 4, "d": 8, "c": 8, "z": 16}[t]
+    bufs = [torch.empty(n * n * esz, dtype=torch.uint8, device="cuda") for _ in range(3)]
+    fill = getattr(lib, f"jb_{t}fill_uniform")
+    for i, b in enumerate(bufs[:2]):
+        if t in "sd":
+            check(fill(b.data_ptr(), n, n, n, 0, 0, seed + i, 0, 0.0), "fill")
+        else:
+            check(fill(b.data_ptr(), n, n, n, 0, 0, seed + i), "fill")
+    gemm = getattr(lib, f"cblas_{t}gemm")
+    if t in "sd":
+        al, be, keep = 1.0, 0.0, None
+    else:
+        keep = np.array([1.0, 0.0], dtype=np.complex64 if t == "c" else np.complex128)
+        al, be = keep.ctypes.data, keep.ctypes.data + keep.itemsize
+
+    def run():
+        gemm(102, 111, 111, n, n, n, al, bufs[0].data_ptr(), n, bufs[1].data_ptr(), n, be, bufs[2].data_ptr(), n)
+
+    run(); torch.cuda.synchronize(); check_last("gemm")
+    s = torch.cuda.current_stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(s)
+    for _ in range(reps):
+        run()
+    e1.record(s); torch.cuda.synchronize()
+    flop = (8.0 if t in "cz" else 2.0) * n ** 3
+    return e0.elapsed_time(e1) / reps, flop

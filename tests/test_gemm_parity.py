@@ -180,3 +180,11 @@ def test_bad_arguments_are_recorded_not_fatal(gpu, rng):
     lib.cblas_dgemm(103, 111, 111, 4, 4, 4, 1.0, A.ctypes.data, 4, A.ctypes.data, 4, 0.0, C0.ctypes.data, 4)  # bad order
     assert lib.jb_last_error() == JB_ERR_ARG
     np.testing.assert_array_equal(C0, A)
+
+
+@pytest.mark.parametrize("ta,tb", [(111, 111), (112, 111), (111, 113), (113, 112)])
+def test_zgemm_ragged_large(gpu, blas, rng, ta, tb):
+    """Tile-edge coverage of the complex DMMA kernel (64x128x8 tiles) incl. odd leading dimensions."""
+    m, n, k = 201, 333, 517
+    Cg, Cr, A, B, *_ = run_both(gpu, blas, "z", ta, tb, m, n, k, 0.5 - 1.5j, 1.0 + 0.5j, rng, pad=(1, 3, 2))
+    assert_close("z", k, Cg, Cr, A, B)
