@@ -57,6 +57,10 @@ for _pfx in ("", "jb_"):
     _sig(_pfx + "cblas_dgemm", None, _i, _i, _i, _i, _i, _i, _d, _p, _i, _p, _i, _d, _p, _i)
     _sig(_pfx + "cblas_cgemm", None, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _i, _p, _p, _i)
     _sig(_pfx + "cblas_zgemm", None, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _i, _p, _p, _i)
+    _sig(_pfx + "cblas_strsm", None, _i, _i, _i, _i, _i, _i, _i, _f, _p, _i, _p, _i)
+    _sig(_pfx + "cblas_dtrsm", None, _i, _i, _i, _i, _i, _i, _i, _d, _p, _i, _p, _i)
+    _sig(_pfx + "cblas_ctrsm", None, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _i)
+    _sig(_pfx + "cblas_ztrsm", None, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _i)
     for _t in "sdcz":
         _sig(f"{_pfx}LAPACKE_{_t}gesv", _i, _i, _i, _i, _p, _i, _p, _p, _i)
         _sig(f"{_pfx}LAPACKE_{_t}getrf", _i, _i, _i, _i, _p, _i, _p)

@@ -192,5 +192,7 @@ template <typename T> int getrs_device(char trans, int n, int nrhs, const T *A, 
 template <typename T> int getri_device(int n, T *A, int lda, const int *d_ipiv, int *d_info, cudaStream_t s);
 template <typename T> int potrf_device(char uplo, int n, T *A, int lda, int *d_info, cudaStream_t s);
 template <typename T> int potrs_device(char uplo, int n, int nrhs, const T *A, int lda, T *B, int ldb, cudaStream_t s);
+// side 141 left / 142 right, uplo 121 upper / 122 lower, trans 111/112/113, diag 131 non-unit / 132 unit
+template <typename T> int trsm_device(int side, int uplo, int trans, int diag, int m, int n, T alpha, const T *A, int lda, T *B, int ldb, cudaStream_t s);
 
 }  // namespace jb

@@ -421,33 +421,87 @@ int getri_device(int n, T *A, int lda, const int *d_ipiv, int *d_info, cudaStrea
   return rc;
 }
 
+// One level of the blocked Cholesky with NB = 32 on the nn x nn block at A (global index offset `off` for info).
 template <typename T>
-int potrf_device(char uplo, int n, T *A, int lda, int *d_info, cudaStream_t s) {
-  if (n <= 0) return 0;
-  const int lower = (uplo == 'L' || uplo == 'l');
+static int potrf_nb32(int lower, int nn, T *A, int lda, int *d_info, int off, cudaStream_t s) {
   const T minus1 = Num<T>::neg(Num<T>::one()), one = Num<T>::one();
-  for (int j0 = 0; j0 < n; j0 += NB) {
-    const int jb = (n - j0 < NB) ? (n - j0) : NB;
+  const int tc = Num<T>::cplx ? 113 : 112;
+  for (int j0 = 0; j0 < nn; j0 += NB) {
+    const int jb = (nn - j0 < NB) ? (nn - j0) : NB;
     T *Ajj = A + j0 + (size_t)j0 * lda;
-    potf2_block_kernel<T><<<1, 1024, 0, s>>>(lower, jb, Ajj, lda, d_info, j0);
+    potf2_block_kernel<T><<<1, 1024, 0, s>>>(lower, jb, Ajj, lda, d_info, off + j0);
     count_launch();
-    const int rem = n - j0 - jb;
+    const int rem = nn - j0 - jb;
     if (rem <= 0) break;
     int rc;
     if (lower) {
       T *A21 = A + (j0 + jb) + (size_t)j0 * lda;
       trsm_small_right_upper_kernel<T><<<(rem + 255) / 256, 256, 0, s>>>(113, jb, rem, Ajj, lda, A21, lda, d_info);
       count_launch();
-      rc = gemm_device<T>(111, Num<T>::cplx ? 113 : 112, rem, rem, jb, minus1, A21, lda, A21, lda, one,
-                          A + (j0 + jb) + (size_t)(j0 + jb) * lda, lda, s, 'L');
+      rc = gemm_device<T>(111, tc, rem, rem, jb, minus1, A21, lda, A21, lda, one, A + (j0 + jb) + (size_t)(j0 + jb) * lda, lda, s, 'L');
     } else {
       T *A12 = A + j0 + (size_t)(j0 + jb) * lda;
       int blocks = (rem + 7) / 8; if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
-      // U12 <- U11^{-H} A12 : effective-lower solve with M = U11^H
-      trsm_small_left_kernel<T><<<blocks, 256, 0, s>>>(1, 0, 113, jb, rem, Ajj, lda, A12, lda, d_info);
+      trsm_small_left_kernel<T><<<blocks, 256, 0, s>>>(1, 0, 113, jb, rem, Ajj, lda, A12, lda, d_info);   // U12 <- U11^{-H} A12
       count_launch();
-      rc = gemm_device<T>(Num<T>::cplx ? 113 : 112, 111, rem, rem, jb, minus1, A12, lda, A12, lda, one,
-                          A + (j0 + jb) + (size_t)(j0 + jb) * lda, lda, s, 'U');
+      rc = gemm_device<T>(tc, 111, rem, rem, jb, minus1, A12, lda, A12, lda, one, A + (j0 + jb) + (size_t)(j0 + jb) * lda, lda, s, 'U');
+    }
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+// Two-level right-looking Cholesky: outer panels of NB2 columns are factorised by the NB=32 routine, the
+// block column (row) below (right of) them is solved 32 columns at a time, and the trailing matrix gets ONE
+// rank-NB2 update per outer step through the tuned GEMM (DMMA for double / complex double) — NB2/32 times
+// fewer sweeps over the trailing matrix than the single-level algorithm.
+template <typename T>
+int potrf_device(char uplo, int n, T *A, int lda, int *d_info, cudaStream_t s) {
+  if (n <= 0) return 0;
+  const int lower = (uplo == 'L' || uplo == 'l');
+  const T minus1 = Num<T>::neg(Num<T>::one()), one = Num<T>::one();
+  const int tc = Num<T>::cplx ? 113 : 112;
+  int NB2 = option("potrf.nb2");
+  // measured (tools/time_lapack.py): single level wins below ~4096 (launch bound), two levels above
+  if (NB2 <= 0) NB2 = (n >= 16384) ? 512 : (n >= 4096 ? 256 : n);
+  if (n <= NB2 + NB) { int rc = potrf_nb32<T>(lower, n, A, lda, d_info, 0, s); if (!rc) JB_CUDA(cudaGetLastError()); return rc; }
+  for (int j0 = 0; j0 < n; j0 += NB2) {
+    const int jb2 = (n - j0 < NB2) ? (n - j0) : NB2;
+    T *Ajj = A + j0 + (size_t)j0 * lda;
+    int rc = potrf_nb32<T>(lower, jb2, Ajj, lda, d_info, j0, s);
+    if (rc) return rc;
+    const int rem = n - j0 - jb2;
+    if (rem <= 0) break;
+    if (lower) {
+      T *A21 = A + (j0 + jb2) + (size_t)j0 * lda;          // rem x jb2 :  A21 <- A21 * L11^{-H}
+      for (int c0 = 0; c0 < jb2; c0 += NB) {
+        const int cb = (jb2 - c0 < NB) ? (jb2 - c0) : NB;
+        trsm_small_right_upper_kernel<T><<<(rem + 255) / 256, 256, 0, s>>>(113, cb, rem, Ajj + c0 + (size_t)c0 * lda, lda,
+                                                                          A21 + (size_t)c0 * lda, lda, d_info);
+        count_launch();
+        const int right = jb2 - c0 - cb;
+        if (right > 0) {   // A21[:, c0+cb:] -= X * L11[c0+cb:, c0:c0+cb]^H
+          rc = gemm_device<T>(111, tc, rem, right, cb, minus1, A21 + (size_t)c0 * lda, lda, Ajj + (c0 + cb) + (size_t)c0 * lda, lda,
+                              one, A21 + (size_t)(c0 + cb) * lda, lda, s, 0);
+          if (rc) return rc;
+        }
+      }
+      rc = gemm_device<T>(111, tc, rem, rem, jb2, minus1, A21, lda, A21, lda, one, A + (j0 + jb2) + (size_t)(j0 + jb2) * lda, lda, s, 'L');
+    } else {
+      T *A12 = A + j0 + (size_t)(j0 + jb2) * lda;          // jb2 x rem :  A12 <- U11^{-H} * A12
+      int blocks = (rem + 7) / 8; if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
+      for (int r0 = 0; r0 < jb2; r0 += NB) {
+        const int rb = (jb2 - r0 < NB) ? (jb2 - r0) : NB;
+        trsm_small_left_kernel<T><<<blocks, 256, 0, s>>>(1, 0, 113, rb, rem, Ajj + r0 + (size_t)r0 * lda, lda, A12 + r0, lda, d_info);
+        count_launch();
+        const int below = jb2 - r0 - rb;
+        if (below > 0) {   // A12[r0+rb:, :] -= U11[r0:r0+rb, r0+rb:]^H * X
+          rc = gemm_device<T>(tc, 111, below, rem, rb, minus1, Ajj + r0 + (size_t)(r0 + rb) * lda, lda, A12 + r0, lda, one,
+                              A12 + r0 + rb, lda, s, 0);
+          if (rc) return rc;
+        }
+      }
+      rc = gemm_device<T>(tc, 111, rem, rem, jb2, minus1, A12, lda, A12, lda, one, A + (j0 + jb2) + (size_t)(j0 + jb2) * lda, lda, s, 'U');
     }
     if (rc) return rc;
   }
@@ -470,12 +524,77 @@ int potrs_device(char uplo, int n, int nrhs, const T *A, int lda, T *B, int ldb,
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// cblas_?trsm on the device (column-major): B <- alpha * op(A)^{-1} B (Left) or alpha * B op(A)^{-1} (Right).
+// Level-3 sibling the factorisations need anyway (BlasOps.trsm, /root/reference/Numeric/Jalla/Foreign/BlasOps.hs:57;
+// SURVEY.md §8f rank 3).  uplo 121 upper / 122 lower, trans 111/112/113, diag 131 non-unit / 132 unit.
+template <typename T>
+__global__ void scale_kernel(int m, int n, T alpha, T *B, int ldb) {
+  for (int j = blockIdx.y; j < n; j += gridDim.y)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x)
+      B[(size_t)i + (size_t)j * ldb] = Num<T>::mul(alpha, B[(size_t)i + (size_t)j * ldb]);
+}
+
+template <typename T>
+int trsm_device(int side, int uplo, int trans, int diag, int m, int n, T alpha, const T *A, int lda, T *B, int ldb,
+                cudaStream_t s) {
+  if (m <= 0 || n <= 0) return 0;
+  if (!(Num<T>::re(alpha) == 1 && Num<T>::im(alpha) == 0)) {
+    dim3 grid((unsigned)min((m + 255) / 256, 1024), (unsigned)min(n, 4096));
+    scale_kernel<T><<<grid, 256, 0, s>>>(m, n, alpha, B, ldb);
+    count_launch();
+  }
+  if (!Num<T>::cplx && trans == 113) trans = 112;
+  const int stored_lower = (uplo == 122), unit = (diag == 132);
+  if (side == 141) return trsm_left_blocked<T>(stored_lower, trans, unit, m, n, A, lda, B, ldb, s);
+  // Right side: X op(A) = B.  Column-block sweep: effective-upper op(A) runs left to right, effective-lower
+  // right to left; each step solves a 32-wide column block against the diagonal block (one thread per row of
+  // B) and updates the remaining columns with one GEMM.
+  const int eff_upper = (trans == 111) ? !stored_lower : stored_lower;
+  const int nblk = (n + NB - 1) / NB;
+  const T minus1 = Num<T>::neg(Num<T>::one()), one = Num<T>::one();
+  if (unit || !eff_upper) {
+    // less common variants: solve the transposed left-side system  op(A)^T X^T = B^T  through a scratch transpose
+    T *W = nullptr;
+    const int ldw = n + (n & 1);
+    if (int rc = ws_alloc((void **)&W, sizeof(T) * (size_t)ldw * m, s)) return rc;
+    int rc = lacpy_device<T>(112, m, n, B, ldb, W, ldw, s);
+    // (X op(A))^T = op(A)^T X^T : transposing flips the trans flag (conj-trans <-> plain conj is handled by
+    // conjugating through the transpose copy for 113)
+    int t2 = (trans == 111) ? 112 : 111;
+    if (trans == 113) {   // op(A) = A^H: A^H^T = conj(A): solve conj(A) Y = B^T  <=>  A conj(Y) = conj(B^T)
+      rc = rc ? rc : lacpy_device<T>(113, m, n, B, ldb, W, ldw, s);
+      t2 = 111;
+    }
+    if (!rc) rc = trsm_left_blocked<T>(stored_lower, t2, unit, n, m, A, lda, W, ldw, s);
+    if (!rc) rc = lacpy_device<T>(trans == 113 ? 113 : 112, n, m, W, ldw, B, ldb, s);
+    ws_free(W, s);
+    return rc;
+  }
+  for (int bi = 0; bi < nblk; bi++) {
+    const int c0 = bi * NB, cb = (n - c0 < NB) ? (n - c0) : NB;
+    trsm_small_right_upper_kernel<T><<<(m + 255) / 256, 256, 0, s>>>(trans, cb, m, A + c0 + (size_t)c0 * lda, lda,
+                                                                    B + (size_t)c0 * ldb, ldb, nullptr);
+    count_launch();
+    const int right = n - c0 - cb;
+    if (right > 0) {   // B[:, c0+cb:] -= X * op(A)[c0:c0+cb, c0+cb:]
+      const T *Ab = (trans == 111) ? A + c0 + (size_t)(c0 + cb) * lda : A + (c0 + cb) + (size_t)c0 * lda;
+      int rc = gemm_device<T>(111, trans, m, right, cb, minus1, B + (size_t)c0 * ldb, ldb, Ab, lda, one,
+                              B + (size_t)(c0 + cb) * ldb, ldb, s, 0);
+      if (rc) return rc;
+    }
+  }
+  JB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 #define INST(T)                                                                                        \
   template int getrf_device<T>(int, int, T *, int, int *, int *, cudaStream_t);                        \
   template int getrs_device<T>(char, int, int, const T *, int, const int *, T *, int, cudaStream_t);   \
   template int getri_device<T>(int, T *, int, const int *, int *, cudaStream_t);                       \
   template int potrf_device<T>(char, int, T *, int, int *, cudaStream_t);                              \
-  template int potrs_device<T>(char, int, int, const T *, int, T *, int, cudaStream_t);
+  template int potrs_device<T>(char, int, int, const T *, int, T *, int, cudaStream_t);              \
+  template int trsm_device<T>(int, int, int, int, int, int, T, const T *, int, T *, int, cudaStream_t);
 INST(float)
 INST(double)
 INST(cfloat)

@@ -59,6 +59,18 @@ class Backend:
             sc = np.array([alpha, beta], dtype=NP[t])
             f(order, ta, tb, m, n, k, sc.ctypes.data, _ptr(A), lda, _ptr(B), ldb, sc.ctypes.data + sc.itemsize, _ptr(Cm), ldc)
 
+    # cblas_?trsm (OpenBLAS backends only; the C restatement has no trsm)
+    def trsm(self, t, order, side, uplo, trans, diag, m, n, alpha, A, lda, B, ldb):
+        name = self._gemm_name(t).replace("gemm", "trsm")
+        if t in "sd":
+            sc = C.c_float if t == "s" else C.c_double
+            f = self._fn(("trsm", t), name, None, [_i] * 7 + [sc, _p, _i, _p, _i])
+            f(order, side, uplo, trans, diag, m, n, alpha, _ptr(A), lda, _ptr(B), ldb)
+        else:
+            f = self._fn(("trsm", t), name, None, [_i] * 7 + [_p, _p, _i, _p, _i])
+            sc = np.array([alpha], dtype=NP[t])
+            f(order, side, uplo, trans, diag, m, n, sc.ctypes.data, _ptr(A), lda, _ptr(B), ldb)
+
     def gesv(self, t, order, n, nrhs, a, lda, ipiv, b, ldb):
         f = self._fn(("gesv", t), self._lapacke_name(t, "gesv"), _i, [_i, _i, _i, _p, _i, _p, _p, _i])
         return f(order, n, nrhs, _ptr(a), lda, _ptr(ipiv), _ptr(b), ldb)

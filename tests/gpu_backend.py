@@ -70,6 +70,14 @@ class GpuBackend:
             al, be = keep.ctypes.data, keep.ctypes.data + keep.itemsize
         self._run(fn, [order, ta, tb, m, n, k, al, A, lda, B, ldb, be, Cm, ldc], {7, 9, 12}, {12}, "gemm", returns_info=False)
 
+    def trsm(self, t, order, side, uplo, trans, diag, m, n, alpha, A, lda, B, ldb):
+        fn = getattr(lib, f"cblas_{t}trsm")
+        if t in "sd":
+            al, keep = alpha, None
+        else:
+            keep = np.array([alpha], dtype=NP[t]); al = keep.ctypes.data
+        self._run(fn, [order, side, uplo, trans, diag, m, n, al, A, lda, B, ldb], {8, 10}, {10}, "trsm", returns_info=False)
+
     def gesv(self, t, order, n, nrhs, a, lda, ipiv, b, ldb):
         return self._run(getattr(lib, f"LAPACKE_{t}gesv"), [order, n, nrhs, a, lda, ipiv, b, ldb], {3, 6}, {3, 5, 6}, "gesv")
 

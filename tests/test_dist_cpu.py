@@ -88,3 +88,110 @@ def test_summa_schedule_gloo(world):
         assert p.exitcode == 0
     assert sorted(r for r, _ in res) == list(range(world))
     assert max(e for _, e in res) < 1e-12
+
+
+# ------------------------------------------------------------------ distributed Cholesky choreography
+class NumpyOps:
+    """CPU stand-in for jalla_b200.dist_chol.DeviceOps (test-only): same interface on CPU torch tensors."""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+
+    def empty(self, nelem):
+        return self.torch.full((max(int(nelem), 1),), float("nan"), dtype=self.torch.float64)
+
+    def zeros(self, nelem):
+        return self.torch.zeros(max(int(nelem), 1), dtype=self.torch.float64)
+
+    @staticmethod
+    def _v(t, off, ld, m, n):
+        a = t.numpy()
+        return np.lib.stride_tricks.as_strided(a[off:], shape=(m, n), strides=(8, 8 * ld)) if m * n else np.zeros((m, n))
+
+    def fill_spd_tile(self, t, off, ld, nb, I, J, seed, diag):
+        from jalla_b200 import synth
+        self._v(t, off, ld, nb, nb)[...] = synth.uniform(nb, nb, seed, "d", I * nb, J * nb, sym=True, diag=float(diag))
+
+    def potrf(self, t, off, ld, nb):
+        v = self._v(t, off, ld, nb, nb)
+        try:
+            L = np.linalg.cholesky(np.tril(v) + np.tril(v, -1).T)
+        except np.linalg.LinAlgError:
+            return 1
+        v[np.tril_indices(nb)] = L[np.tril_indices(nb)]
+        return 0
+
+    def trsm_right_lt(self, m, nb, L, offl, ldl, B, offb, ldb):
+        Lm = np.tril(self._v(L, offl, ldl, nb, nb)); Bv = self._v(B, offb, ldb, m, nb)
+        Bv[...] = np.linalg.solve(Lm, Bv.T).T
+
+    def trsm_left(self, trans, nb, nrhs, L, offl, ldl, B, offb, ldb):
+        Lm = np.tril(self._v(L, offl, ldl, nb, nb)); Bv = self._v(B, offb, ldb, nb, nrhs)
+        Bv[...] = np.linalg.solve(Lm if trans == 111 else Lm.T, Bv)
+
+    def gemm(self, ta, tb, m, n, k, alpha, A, offa, lda, B, offb, ldb, beta, Cm, offc, ldc):
+        Av = self._v(A, offa, lda, m, k) if ta == 111 else self._v(A, offa, lda, k, m).T
+        Bv = self._v(B, offb, ldb, k, n) if tb == 111 else self._v(B, offb, ldb, n, k).T
+        Cv = self._v(Cm, offc, ldc, m, n)
+        Cv[...] = alpha * (Av @ Bv) + (beta * Cv if beta != 0 else 0.0)
+
+    def copy(self, m, n, A, offa, lda, B, offb, ldb):
+        self._v(B, offb, ldb, m, n)[...] = self._v(A, offa, lda, m, n)
+
+    def finish(self):
+        pass
+
+
+def _chol_worker(rank, world, port, n, nb, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from jalla_b200 import synth
+    from jalla_b200.dist import ProcessGrid
+    from jalla_b200.dist_chol import DistCholesky
+    if world > 1:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        grid = ProcessGrid(world, rank, dist if world > 1 else None)
+        ch = DistCholesky(grid, n, nb, NumpyOps(), seed=11)
+        ch.fill_spd()
+        info = ch.potrf()
+        A = synth.uniform(n, n, 11, "d", sym=True, diag=float(n))
+        Lref = np.linalg.cholesky(A)
+        ops = ch.ops
+        err = 0.0
+        for j in range(ch.Tc):
+            for i in range(ch.Tr):
+                I, J = i * grid.pr + grid.row, j * grid.pc + grid.col
+                if I >= J:
+                    tile = ops._v(ch.A, ch.tile_off(i, j), ch.ld, nb, nb)
+                    ref = Lref[I * nb:(I + 1) * nb, J * nb:(J + 1) * nb]
+                    err = max(err, float(np.abs((np.tril(tile) if I == J else tile) - ref).max()))
+        b = synth.uniform(n, 1, 12, "d")[:, 0]
+        x = torch.from_numpy(b.copy())
+        ch.potrs(x, 1)
+        xerr = float(np.abs(x.numpy() - np.linalg.solve(A, b)).max())
+        res = ch.residual(x, torch.from_numpy(b.copy()), 1)
+        q.put((rank, info, err, xerr, res))
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n,nb", [(1, 48, 16), (2, 80, 16), (4, 96, 16), (8, 176, 16)])
+def test_dist_cholesky_choreography_gloo(world, n, nb):
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_chol_worker, args=(r, world, port, n, nb, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, info, err, xerr, r in res:
+        assert info == 0 and err < 1e-11 and xerr < 1e-11 and r < 10, (rank, info, err, xerr, r)

@@ -226,3 +226,30 @@ def test_host_pointer_solve(gpu_host, orc, rng):
     assert orc.gesv("d", 102, n, 2, Ao, n, po, Bo, n) == 0
     np.testing.assert_array_equal(pg, po)
     assert fro(Bg - Bo) / fro(Bo) <= 1e3 * n * EPS["d"]
+
+
+@pytest.mark.parametrize("t", "dz")
+@pytest.mark.parametrize("uplo", ["L", "U"])
+def test_potrf_two_level(gpu, blas, rng, t, uplo):
+    """n large enough for the two-level (NB2 = 256 outer, 32 inner) Cholesky; ragged on both levels."""
+    from jalla_b200._lib import lib
+    n = 701
+    S = spd(rng, t, n)
+    Sg, Sb = S.copy(order="F"), S.copy(order="F")
+    lib.jb_set_option(b"potrf.nb2", 256)      # force the two-level path at a test-sized n
+    try:
+        assert gpu.potrf(t, 102, uplo, n, Sg, n) == 0
+        Sbad = S.copy(order="F"); Sbad[450, 450] = -5.0
+        assert gpu.potrf(t, 102, uplo, n, Sbad, n) == 451
+    finally:
+        lib.jb_set_option(b"potrf.nb2", 0)
+    assert blas.potrf(t, 102, uplo, n, Sb, n) == 0
+    tri = np.tril_indices(n) if uplo == "L" else np.triu_indices(n)
+    other = np.triu_indices(n, 1) if uplo == "L" else np.tril_indices(n, -1)
+    assert fro(Sg[tri] - Sb[tri]) / fro(Sb[tri]) <= 100 * n * EPS[t]
+    np.testing.assert_array_equal(Sg[other], S[other])
+    F = np.tril(Sg) if uplo == "L" else np.triu(Sg)
+    rec = F @ F.conj().T if uplo == "L" else F.conj().T @ F
+    assert fro(rec - S) / (n * EPS[t] * fro(S)) <= 10
+    Sbad2 = S.copy(order="F"); Sbad2[450, 450] = -5.0
+    assert blas.potrf(t, 102, uplo, n, Sbad2, n) == 451

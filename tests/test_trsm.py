@@ -1,0 +1,46 @@
+"""cblas_?trsm (the level-3 sibling the factorisations and the distributed Cholesky use) against OpenBLAS:
+every side / uplo / trans / diag combination, both orders, blocked sizes."""
+import itertools
+
+import numpy as np
+import pytest
+
+from tests.util import NP, EPS, rand, fro
+
+pytestmark = pytest.mark.gpu
+
+
+def tri_matrix(rng, t, n, ld):
+    A = rand(rng, t, n, n, ld)
+    A[:n, :] += (n * np.eye(n)).astype(NP[t])      # well conditioned triangles
+    return A
+
+
+@pytest.mark.parametrize("t", "sdcz")
+@pytest.mark.parametrize("side,uplo,trans,diag", list(itertools.product((141, 142), (121, 122), (111, 112, 113), (131, 132))))
+def test_trsm_all_variants(gpu, blas, rng, t, side, uplo, trans, diag):
+    m, n = 77, 53
+    ka = m if side == 141 else n
+    A = tri_matrix(rng, t, ka, ka + 1)
+    B = rand(rng, t, m, n, m + 2)
+    alpha = 0.5 if t in "sd" else 0.5 - 0.25j
+    Bg, Bb = B.copy(order="F"), B.copy(order="F")
+    gpu.trsm(t, 102, side, uplo, trans, diag, m, n, alpha, A, ka + 1, Bg, m + 2)
+    blas.trsm(t, 102, side, uplo, trans, diag, m, n, alpha, A, ka + 1, Bb, m + 2)
+    assert fro(Bg[:m] - Bb[:m]) / fro(Bb[:m]) <= 200 * max(m, n) * EPS[t]
+    assert np.isnan(Bg[m:]).all()
+
+
+@pytest.mark.parametrize("t", "dz")
+def test_trsm_row_major_and_large(gpu, blas, rng, t):
+    m, n = 300, 130
+    for side, uplo, trans in [(142, 122, 113), (141, 121, 111), (142, 121, 111), (141, 122, 112)]:
+        ka = m if side == 141 else n
+        A = tri_matrix(rng, t, ka, ka)
+        for order in (102, 101):
+            B = rand(rng, t, m, n) if order == 102 else rand(rng, t, n, m)
+            ldb = B.shape[0]
+            Bg, Bb = B.copy(order="F"), B.copy(order="F")
+            gpu.trsm(t, order, side, uplo, trans, 131, m, n, 1.0, A, ka, Bg, ldb)
+            blas.trsm(t, order, side, uplo, trans, 131, m, n, 1.0, A, ka, Bb, ldb)
+            assert fro(Bg - Bb) / fro(Bb) <= 500 * max(m, n) * EPS[t], (side, uplo, trans, order)
