@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """BASELINE.json configs[3]: blocked Cholesky potrf + potrs on an N x N SPD Double matrix, 2-D block-cyclic over
 the launched ranks (torchrun, one rank per GPU; also runs single-GPU).  Prints one JSON line (rank 0).
-    python -m torch.distributed.run --nproc-per-node 8 tools/bench_chol.py --n 65536 --nb 512"""
+    python -m torch.distributed.run --nproc-per-node 8 tools/bench_chol.py --size 65536 --tile 512"""
 import argparse, ctypes as C, json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -10,8 +10,8 @@ from jalla_b200.dist import ProcessGrid
 from jalla_b200.dist_chol import DistCholesky, DeviceOps
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--n", type=int, default=65536)
-ap.add_argument("--nb", type=int, default=512)
+ap.add_argument("--size", dest="n", type=int, default=65536)
+ap.add_argument("--tile", dest="nb", type=int, default=512)
 ap.add_argument("--reps", type=int, default=1)
 args = ap.parse_args()
 world, rank, lr = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
