@@ -58,93 +58,98 @@ class ProcessGrid:
                     self.col_group = g
 
 
-def gemm_plan(n: int, pr: int, pc: int, row: int, col: int):
+def gemm_plan(n: int, pr: int, pc: int, row: int, col: int, chunks: int = 16):
     """Static description of rank (row,col)'s share of C = A*B (all sizes in elements).
-    Returns dict with block sizes, the broadcast schedule and, per local GEMM p, which A
-    panels must have arrived."""
+    K is cut into `chunks` panels of width w (a divisor of both owners' K blocks); panel t of A lives on process
+    column (t*w)//kc and panel t of B on process row (t*w)//kr.  Each panel is one broadcast and one local GEMM,
+    so only the first panel's transfer is exposed; everything else hides under the DMMA GEMMs."""
     assert n % pr == 0 and n % pc == 0, "N must divide the process grid"
     mb, nb, kr, kc = n // pr, n // pc, n // pr, n // pc
-    gemms = []
-    for p in range(pr):
-        k0, k1 = p * kr, (p + 1) * kr
-        gemms.append({"p": p, "k0": k0, "k1": k1, "a_panels": list(range(k0 // kc, (k1 - 1) // kc + 1)), "beta": 0.0 if p == 0 else 1.0})
-    return {"mb": mb, "nb": nb, "kr": kr, "kc": kc, "row0": row * mb, "col0": col * nb,
-            "a_bcasts": [(q, row * pc + q) for q in range(pc)], "b_bcasts": [(p, p * pc + col) for p in range(pr)],
-            "gemms": gemms}
+    nt = max(chunks, pr, pc)
+    while n % nt or kr % (n // nt) or kc % (n // nt):
+        nt += 1
+    w = n // nt
+    panels = []
+    for t in range(nt):
+        k0 = t * w
+        panels.append({"t": t, "k0": k0, "k1": k0 + w, "a_src": row * pc + k0 // kc, "b_src": (k0 // kr) * pc + col,
+                       "a_mine": k0 // kc == col, "b_mine": k0 // kr == row, "beta": 0.0 if t == 0 else 1.0})
+    return {"mb": mb, "nb": nb, "kr": kr, "kc": kc, "w": w, "row0": row * mb, "col0": col * nb, "panels": panels,
+            "gemms": panels}
 
 
-def summa_step(plan, grid: ProcessGrid, a_blocks, b_blocks, local_gemm):
+def summa_step(plan, grid: ProcessGrid, a_panels, b_panels, local_gemm):
     """One distributed product: post every panel broadcast (A panels along the process row, B panels along
-    the process column, all asynchronous), then run the local GEMMs in K order, each waiting only for the
-    panels it consumes.  Backend agnostic (NCCL on GPUs; gloo in the CPU tests): `a_blocks[q]` / `b_blocks[p]`
-    are the tensors panels land in (the owner's slot already holds its data), `local_gemm(g)` runs one
-    entry of plan["gemms"]."""
+    the process column, all asynchronous, in K order), then run the local GEMMs in K order, each waiting only
+    for the two panels it consumes.  Backend agnostic (NCCL on GPUs; gloo in the CPU tests): `a_panels[t]` /
+    `b_panels[t]` are the tensors panels land in (the owner's slots already hold its data), `local_gemm(p)`
+    runs one entry of plan["panels"]."""
     dist = grid.dist
     a_work, b_work = {}, {}
-    for q, src in plan["a_bcasts"]:
-        a_work[q] = dist.broadcast(a_blocks[q], src=src, group=grid.row_group, async_op=True) if grid.pc > 1 else None
-    for p, src in plan["b_bcasts"]:
-        b_work[p] = dist.broadcast(b_blocks[p], src=src, group=grid.col_group, async_op=True) if grid.pr > 1 else None
-    for g in plan["gemms"]:
-        for q in g["a_panels"]:
-            if a_work.get(q) is not None:
-                a_work[q].wait(); a_work[q] = None
-        if b_work.get(g["p"]) is not None:
-            b_work[g["p"]].wait(); b_work[g["p"]] = None
-        local_gemm(g)
-    for w in list(a_work.values()) + list(b_work.values()):
-        if w is not None:
-            w.wait()
+    for p in plan["panels"]:
+        t = p["t"]
+        a_work[t] = dist.broadcast(a_panels[t], src=p["a_src"], group=grid.row_group, async_op=True) if grid.pc > 1 else None
+        b_work[t] = dist.broadcast(b_panels[t], src=p["b_src"], group=grid.col_group, async_op=True) if grid.pr > 1 else None
+    for p in plan["panels"]:
+        t = p["t"]
+        if a_work[t] is not None:
+            a_work[t].wait()
+        if b_work[t] is not None:
+            b_work[t].wait()
+        local_gemm(p)
 
 
 class ShardedGemm:
-    """configs[1]: one FP64 N x N x N product, 2-D sharded; a step = broadcasts + local GEMMs."""
+    """configs[1]: one FP64 N x N x N product, 2-D sharded; a step = panel broadcasts + local GEMMs."""
 
     def __init__(self, grid: ProcessGrid, n: int, seed: int):
         import torch
         from ._lib import lib, check
         self.torch, self.lib, self.check = torch, lib, check
         self.grid, self.n, self.seed = grid, n, seed
-        self.plan = gemm_plan(n, grid.pr, grid.pc, grid.row, grid.col)
+        self.plan = gemm_plan(n, grid.pr, grid.pc, grid.row, grid.col, chunks=1 if grid.world == 1 else 16)
         P = self.plan
         dev = torch.device("cuda", torch.cuda.current_device())
         f64 = torch.float64
-        # column-major blocks held as flat device buffers
-        self.A_row = torch.empty(P["mb"] * n, dtype=f64, device=dev)              # mb x n, ld = mb
-        self.B_blk = [torch.empty(P["kr"] * P["nb"], dtype=f64, device=dev) for _ in range(grid.pr)]   # kr x nb each
-        self.C = torch.empty(P["mb"] * P["nb"], dtype=f64, device=dev)
-        # generate only the blocks this rank OWNS; the rest arrives by broadcast
-        self.A_own = self.A_row[grid.col * P["kc"] * P["mb"]:(grid.col + 1) * P["kc"] * P["mb"]]
-        self.B_own = self.B_blk[grid.row]
-        check(lib.jb_dfill_uniform(self.A_own.data_ptr(), P["mb"], P["mb"], P["kc"], P["row0"], grid.col * P["kc"], seed, 0, 0.0), "fill A")
-        check(lib.jb_dfill_uniform(self.B_own.data_ptr(), P["kr"], P["kr"], P["nb"], grid.row * P["kr"], P["col0"], seed + 1, 0, 0.0), "fill B")
+        mb, nb, w = P["mb"], P["nb"], P["w"]
+        # column-major blocks held as flat device buffers: A row block mb x n (ld = mb; a K panel is a contiguous
+        # slice), B as one w x nb buffer per K panel (ld = w)
+        self.A_row = torch.empty(mb * n, dtype=f64, device=dev)
+        self.a_panels = [self.A_row[p["k0"] * mb:p["k1"] * mb] for p in P["panels"]]
+        self.b_panels = [torch.empty(w * nb, dtype=f64, device=dev) for _ in P["panels"]]
+        self.C = torch.empty(mb * nb, dtype=f64, device=dev)
+        # generate only the panels this rank OWNS; the rest arrives by broadcast
+        for p in P["panels"]:
+            if p["a_mine"]:
+                check(lib.jb_dfill_uniform(self.a_panels[p["t"]].data_ptr(), mb, mb, w, P["row0"], p["k0"], seed, 0, 0.0), "fill A")
+            if p["b_mine"]:
+                check(lib.jb_dfill_uniform(self.b_panels[p["t"]].data_ptr(), w, w, nb, p["k0"], P["col0"], seed + 1, 0, 0.0), "fill B")
         torch.cuda.synchronize()
 
-    def _local_gemm(self, g):
+    def _local_gemm(self, p):
         P, lib = self.plan, self.lib
-        a_ptr = self.A_row.data_ptr() + g["k0"] * P["mb"] * 8
-        lib.cblas_dgemm(102, 111, 111, P["mb"], P["nb"], g["k1"] - g["k0"], 1.0, a_ptr, P["mb"], self.B_blk[g["p"]].data_ptr(), P["kr"],
-                        g["beta"], self.C.data_ptr(), P["mb"])
+        lib.cblas_dgemm(102, 111, 111, P["mb"], P["nb"], P["w"], 1.0, self.a_panels[p["t"]].data_ptr(), P["mb"],
+                        self.b_panels[p["t"]].data_ptr(), P["w"], p["beta"], self.C.data_ptr(), P["mb"])
 
     def step(self):
         P, grid = self.plan, self.grid
         if grid.world == 1:
-            self._local_gemm(P["gemms"][0])
+            for p in P["panels"]:
+                self._local_gemm(p)
             return
-        a_blocks = [self.A_row[q * P["kc"] * P["mb"]:(q + 1) * P["kc"] * P["mb"]] for q in range(grid.pc)]
-        summa_step(P, grid, a_blocks, self.B_blk, self._local_gemm)
+        summa_step(P, grid, self.a_panels, self.b_panels, self._local_gemm)
 
     def kernel_ms(self, reps=3) -> float:
         """Average duration of this rank's local GEMM work (all K panels) with CUDA events, no collectives."""
         torch = self.torch
         s = torch.cuda.current_stream()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        for g in self.plan["gemms"]:
+        for g in self.plan["panels"]:
             self._local_gemm(g)
         torch.cuda.synchronize()
         e0.record(s)
         for _ in range(reps):
-            for g in self.plan["gemms"]:
+            for g in self.plan["panels"]:
                 self._local_gemm(g)
         e1.record(s)
         torch.cuda.synchronize()
@@ -179,7 +184,7 @@ class ShardedGemm:
                 return {"value": None, "unit": "TFLOP/s", "error": "pinned allocation failed"}
             try:
                 self.check(lib.jb_memcpy_d2h(hA, self.A_row.data_ptr(), nbytes), "d2h A")
-                self.check(lib.jb_memcpy_d2h(hB, self.B_blk[0].data_ptr(), nbytes), "d2h B")
+                self.check(lib.jb_memcpy_d2h(hB, self.b_panels[0].data_ptr(), nbytes), "d2h B")
                 lib.cblas_dgemm(102, 111, 111, n, n, n, 1.0, hA, n, hB, n, 0.0, hC, n)   # warm-up (pool, streams)
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
@@ -202,13 +207,16 @@ class ShardedGemm:
                     "h2d_bytes_per_step": 2 * nbytes, "d2h_bytes_per_step": nbytes,
                     "path": "cblas_dgemm(host pinned A,B,C): panel-pipelined H2D / DMMA / D2H inside the call"}
         # multi-GPU: host shards -> device, distributed step, C block -> host
-        hA = torch.empty(self.A_own.numel(), dtype=torch.float64, pin_memory=True); hA.copy_(self.A_own)
-        hB = torch.empty(self.B_own.numel(), dtype=torch.float64, pin_memory=True); hB.copy_(self.B_own)
+        own_a = [self.a_panels[p["t"]] for p in P["panels"] if p["a_mine"]]
+        own_b = [self.b_panels[p["t"]] for p in P["panels"] if p["b_mine"]]
+        hA = [torch.empty(t.numel(), dtype=torch.float64, pin_memory=True).copy_(t) for t in own_a]
+        hB = [torch.empty(t.numel(), dtype=torch.float64, pin_memory=True).copy_(t) for t in own_b]
         hC = torch.empty(self.C.numel(), dtype=torch.float64, pin_memory=True)
         dist = grid.dist
 
         def one():
-            self.A_own.copy_(hA, non_blocking=True); self.B_own.copy_(hB, non_blocking=True)
+            for d, h in zip(own_a + own_b, hA + hB):
+                d.copy_(h, non_blocking=True)
             self.step()
             hC.copy_(self.C, non_blocking=True)
 
@@ -222,7 +230,7 @@ class ShardedGemm:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         ms = float(ms.item())
         return {"value": 2.0 * n ** 3 / (ms * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": ms,
-                "h2d_bytes_per_step": (hA.numel() + hB.numel()) * 8 * grid.world, "d2h_bytes_per_step": hC.numel() * 8 * grid.world,
+                "h2d_bytes_per_step": sum(t.numel() for t in hA + hB) * 8 * grid.world, "d2h_bytes_per_step": hC.numel() * 8 * grid.world,
                 "path": "pinned host shards -> H2D -> NCCL panel broadcasts + cblas_dgemm panels -> D2H of the C block"}
 
 

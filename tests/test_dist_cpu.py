@@ -32,12 +32,14 @@ def test_gemm_plan_covers_k_exactly():
     for world in (1, 2, 4, 8):
         pr, pc = grid_shape(world)
         for r in range(world):
-            P = gemm_plan(n, pr, pc, r // pc, r % pc)
-            ks = sorted((g["k0"], g["k1"]) for g in P["gemms"])
+            P = gemm_plan(n, pr, pc, r // pc, r % pc, chunks=8)
+            ks = [(g["k0"], g["k1"]) for g in P["panels"]]
             assert ks[0][0] == 0 and ks[-1][1] == n and all(a[1] == b[0] for a, b in zip(ks, ks[1:]))
-            assert P["gemms"][0]["beta"] == 0.0 and all(g["beta"] == 1.0 for g in P["gemms"][1:])
-            for g in P["gemms"]:   # the A panels named cover the K range of the step
-                assert g["a_panels"][0] * P["kc"] <= g["k0"] and (g["a_panels"][-1] + 1) * P["kc"] >= g["k1"]
+            assert P["panels"][0]["beta"] == 0.0 and all(g["beta"] == 1.0 for g in P["panels"][1:])
+            for g in P["panels"]:   # a panel never straddles an ownership boundary, and its owners sit in my row / column
+                assert g["k0"] // P["kc"] == (g["k1"] - 1) // P["kc"] and g["k0"] // P["kr"] == (g["k1"] - 1) // P["kr"]
+                assert g["a_src"] // pc == r // pc and g["b_src"] % pc == r % pc
+                assert g["a_mine"] == (g["a_src"] == r) and g["b_mine"] == (g["b_src"] == r)
 
 
 def _worker(rank, world, port, n, q):
@@ -50,22 +52,25 @@ def _worker(rank, world, port, n, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         grid = ProcessGrid(world, rank, dist)
-        P = gemm_plan(n, grid.pr, grid.pc, grid.row, grid.col)
-        mb, nb, kr, kc = P["mb"], P["nb"], P["kr"], P["kc"]
-        # column-major blocks as flat tensors; only the owned block is filled
-        a_blocks = [torch.zeros(mb * kc, dtype=torch.float64) for _ in range(grid.pc)]
-        b_blocks = [torch.zeros(kr * nb, dtype=torch.float64) for _ in range(grid.pr)]
-        a_blocks[grid.col].copy_(torch.from_numpy(synth.uniform(mb, kc, 7, "d", P["row0"], grid.col * kc).T.copy().ravel()))
-        b_blocks[grid.row].copy_(torch.from_numpy(synth.uniform(kr, nb, 8, "d", grid.row * kr, P["col0"]).T.copy().ravel()))
+        P = gemm_plan(n, grid.pr, grid.pc, grid.row, grid.col, chunks=6)
+        mb, nb, w = P["mb"], P["nb"], P["w"]
+        # column-major panels as flat tensors; only the owned panels are filled
+        a_panels = [torch.zeros(mb * w, dtype=torch.float64) for _ in P["panels"]]
+        b_panels = [torch.zeros(w * nb, dtype=torch.float64) for _ in P["panels"]]
+        for p in P["panels"]:
+            if p["a_mine"]:
+                a_panels[p["t"]].copy_(torch.from_numpy(synth.uniform(mb, w, 7, "d", P["row0"], p["k0"]).T.copy().ravel()))
+            if p["b_mine"]:
+                b_panels[p["t"]].copy_(torch.from_numpy(synth.uniform(w, nb, 8, "d", p["k0"], P["col0"]).T.copy().ravel()))
         Cacc = np.zeros((mb, nb))
 
-        def local_gemm(g):
+        def local_gemm(p):
             nonlocal Cacc
-            A_row = np.concatenate([b.numpy().reshape(kc, mb).T for b in a_blocks], axis=1)   # mb x n
-            Bp = b_blocks[g["p"]].numpy().reshape(nb, kr).T                                       # kr x nb
-            Cacc = g["beta"] * Cacc + A_row[:, g["k0"]:g["k1"]] @ Bp
+            Ap = a_panels[p["t"]].numpy().reshape(w, mb).T      # mb x w
+            Bp = b_panels[p["t"]].numpy().reshape(nb, w).T      # w x nb
+            Cacc = p["beta"] * Cacc + Ap @ Bp
 
-        summa_step(P, grid, a_blocks, b_blocks, local_gemm)
+        summa_step(P, grid, a_panels, b_panels, local_gemm)
         A = synth.uniform(n, n, 7, "d"); B = synth.uniform(n, n, 8, "d")
         want = (A @ B)[P["row0"]:P["row0"] + mb, P["col0"]:P["col0"] + nb]
         q.put((rank, float(np.abs(Cacc - want).max())))
@@ -73,7 +78,7 @@ def _worker(rank, world, port, n, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_summa_schedule_gloo(world):
     import torch.multiprocessing as mp
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()

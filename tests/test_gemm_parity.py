@@ -188,3 +188,14 @@ def test_zgemm_ragged_large(gpu, blas, rng, ta, tb):
     m, n, k = 201, 333, 517
     Cg, Cr, A, B, *_ = run_both(gpu, blas, "z", ta, tb, m, n, k, 0.5 - 1.5j, 1.0 + 0.5j, rng, pad=(1, 3, 2))
     assert_close("z", k, Cg, Cr, A, B)
+
+
+@pytest.mark.parametrize("ta,tb", list(itertools.product((111, 112), (111, 112))))
+def test_sgemm_ragged_large(gpu, blas, rng, ta, tb):
+    """Tile-edge coverage of the FP32 SIMT kernel (128x128x8 tiles, vector loads need ld % 4 == 0)."""
+    m, n, k = 335, 269, 531
+    ra, rb = (m if ta == 111 else k), (k if tb == 111 else n)
+    Cg, Cr, A, B, *_ = run_both(gpu, blas, "s", ta, tb, m, n, k, 1.5, -0.5, rng, pad=((-ra) % 4, 4 + (-rb) % 4, 3))
+    assert_close("s", k, Cg, Cr, A, B)
+    Cg, Cr, A, B, *_ = run_both(gpu, blas, "s", ta, tb, 256, 384, 128, 1.0, 0.0, rng)
+    assert_close("s", 128, Cg, Cr, A, B)
