@@ -6,8 +6,8 @@
 
 namespace jb {
 
-// Large all-host GEMM: stream column panels of B / C through the GPU so the PCIe copies
-// overlap the kernel (the e2e path bench.py times).  Declared here, defined below.
+// Large all-host GEMM: stream row blocks of A and column panels of B / C through the GPU so the PCIe
+// copies overlap the kernel (the e2e path bench.py times).  Declared here, defined below.
 template <typename T>
 static int gemm_host_pipelined(int ta, int tb, int m, int n, int k, T alpha, const T *A, int lda, const T *B, int ldb,
                                T beta, T *C, int ldc, cudaStream_t s);
@@ -68,80 +68,92 @@ static void gemm_entry(const char *name, int order, int ta, int tb, int m, int n
 template <typename T>
 static int gemm_host_pipelined(int ta, int tb, int m, int n, int k, T alpha, const T *A, int lda, const T *B, int ldb,
                                T beta, T *C, int ldc, cudaStream_t s) {
-  // A resident once; B and C move in column panels of op(B)/C on two copy streams,
-  // double buffered, while the compute stream multiplies the previous panel.
+  // C is cut into R row blocks x P column panels.  Copy order on the H2D stream: A block 0, B panel 0, the other B
+  // panels, then the other A blocks; tile (i,j) starts as soon as A block i and B panel j have landed, and its
+  // result leaves on the D2H stream while the next tile multiplies.  PCIe moves the operands (2 x N^2) faster than
+  // the GEMM consumes them, so after the first tile's operands the copies hide completely under the kernel.
   const bool beta0 = Num<T>::is_zero(beta);
-  long ra = (ta == 111) ? m : k, ca = (ta == 111) ? k : m;
-  const int NP = 1024;                       // panel width (columns of C)
-  int npanels = (n + NP - 1) / NP;
-  cudaStream_t sin, sout;
-  JB_CUDA(cudaStreamCreateWithFlags(&sin, cudaStreamNonBlocking));
-  JB_CUDA(cudaStreamCreateWithFlags(&sout, cudaStreamNonBlocking));
-  T *dA = nullptr, *dB[2] = {nullptr, nullptr}, *dC[2] = {nullptr, nullptr};
-  int ldda = (int)(ra + (ra & 1)), lddc = m + (m & 1);
-  // B panel storage: NoTrans -> k x NP (ld k), Trans -> NP x k (ld NP)
-  int lddb = (tb == 111) ? (k + (k & 1)) : NP;
-  size_t bpanel = (tb == 111) ? (size_t)lddb * NP : (size_t)lddb * k;
-  cudaEvent_t ev_in[2], ev_done[2], ev_out[2], ev_start;
+  const int R = (m >= 8192) ? 2 : 1;
+  const int MB = ((m + R - 1) / R + 127) / 128 * 128;          // rows of op(A)/C per block
+  const int NP = 2048;                                         // columns of C per panel
+  const int nblocks = (m + MB - 1) / MB, npanels = (n + NP - 1) / NP;
+  const long ra = (ta == 111) ? m : k, ca = (ta == 111) ? k : m;
+  const long rb = (tb == 111) ? k : n, cb = (tb == 111) ? n : k;
+  const int ldda = (int)(ra + (ra & 1)), lddb = (int)(rb + (rb & 1)), lddc = m + (m & 1);
+  cudaStream_t sin = nullptr, sout = nullptr;
+  T *dA = nullptr, *dB = nullptr, *dC = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_tile = nullptr;
+  cudaEvent_t *ev_a = nullptr, *ev_b = nullptr;
   int rc = 0;
   cudaError_t e = cudaSuccess;
 #define PL_CUDA(x) do { e = (x); if (e != cudaSuccess) { set_error(JB_ERR_CUDA, "gemm (host pipeline): %s", cudaGetErrorString(e)); rc = JB_ERR_CUDA; goto done; } } while (0)
-  for (int i = 0; i < 2; i++) { ev_in[i] = ev_done[i] = ev_out[i] = nullptr; }
-  ev_start = nullptr;
-  PL_CUDA(cudaMalloc(&dA, (size_t)ldda * ca * sizeof(T)));
-  for (int i = 0; i < 2; i++) {
-    PL_CUDA(cudaMalloc(&dB[i], bpanel * sizeof(T)));
-    PL_CUDA(cudaMalloc(&dC[i], (size_t)lddc * NP * sizeof(T)));
-    PL_CUDA(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
-    PL_CUDA(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming));
-    PL_CUDA(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
-  }
+  ev_a = new cudaEvent_t[nblocks]();
+  ev_b = new cudaEvent_t[npanels]();
+  PL_CUDA(cudaStreamCreateWithFlags(&sin, cudaStreamNonBlocking));
+  PL_CUDA(cudaStreamCreateWithFlags(&sout, cudaStreamNonBlocking));
+  if ((rc = ws_alloc((void **)&dA, (size_t)ldda * ca * sizeof(T), s))) goto done;
+  if ((rc = ws_alloc((void **)&dB, (size_t)lddb * cb * sizeof(T), s))) goto done;
+  if ((rc = ws_alloc((void **)&dC, (size_t)lddc * n * sizeof(T), s))) goto done;
+  for (int i = 0; i < nblocks; i++) PL_CUDA(cudaEventCreateWithFlags(&ev_a[i], cudaEventDisableTiming));
+  for (int j = 0; j < npanels; j++) PL_CUDA(cudaEventCreateWithFlags(&ev_b[j], cudaEventDisableTiming));
   PL_CUDA(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
-  PL_CUDA(cudaEventRecord(ev_start, s));
+  PL_CUDA(cudaEventCreateWithFlags(&ev_tile, cudaEventDisableTiming));
+  PL_CUDA(cudaEventRecord(ev_start, s));                       // buffers come from s's pool: order the side streams after it
   PL_CUDA(cudaStreamWaitEvent(sin, ev_start, 0));
   PL_CUDA(cudaStreamWaitEvent(sout, ev_start, 0));
-  PL_CUDA(cudaMemcpy2DAsync(dA, (size_t)ldda * sizeof(T), A, (size_t)lda * sizeof(T), (size_t)ra * sizeof(T), (size_t)ca,
-                            cudaMemcpyHostToDevice, sin));
-  for (int p = 0; p < npanels; p++) {
-    int b = p & 1, j0 = p * NP, nb = (n - j0 < NP) ? (n - j0) : NP;
-    if (p >= 2) PL_CUDA(cudaStreamWaitEvent(sin, ev_done[b], 0));    // buffer b's previous multiply finished
-    if (tb == 111)
-      PL_CUDA(cudaMemcpy2DAsync(dB[b], (size_t)lddb * sizeof(T), B + (size_t)j0 * ldb, (size_t)ldb * sizeof(T),
-                                (size_t)k * sizeof(T), (size_t)nb, cudaMemcpyHostToDevice, sin));
-    else
-      PL_CUDA(cudaMemcpy2DAsync(dB[b], (size_t)lddb * sizeof(T), B + j0, (size_t)ldb * sizeof(T), (size_t)nb * sizeof(T),
-                                (size_t)k, cudaMemcpyHostToDevice, sin));
-    if (!beta0) {
-      if (p >= 2) PL_CUDA(cudaStreamWaitEvent(sin, ev_out[b], 0));
-      PL_CUDA(cudaMemcpy2DAsync(dC[b], (size_t)lddc * sizeof(T), C + (size_t)j0 * ldc, (size_t)ldc * sizeof(T),
-                                (size_t)m * sizeof(T), (size_t)nb, cudaMemcpyHostToDevice, sin));
+  {
+    auto copy_a = [&](int i) -> cudaError_t {                  // rows [i*MB, ..) of op(A)
+      const int r0 = i * MB, mr = (m - r0 < MB) ? (m - r0) : MB;
+      cudaError_t ce;
+      if (ta == 111) ce = cudaMemcpy2DAsync(dA + r0, (size_t)ldda * sizeof(T), A + r0, (size_t)lda * sizeof(T), (size_t)mr * sizeof(T), (size_t)k, cudaMemcpyHostToDevice, sin);
+      else ce = cudaMemcpy2DAsync(dA + (size_t)r0 * ldda, (size_t)ldda * sizeof(T), A + (size_t)r0 * lda, (size_t)lda * sizeof(T), (size_t)k * sizeof(T), (size_t)mr, cudaMemcpyHostToDevice, sin);
+      if (ce == cudaSuccess && !beta0)
+        ce = cudaMemcpy2DAsync(dC + r0, (size_t)lddc * sizeof(T), C + r0, (size_t)ldc * sizeof(T), (size_t)mr * sizeof(T), (size_t)n, cudaMemcpyHostToDevice, sin);
+      return ce == cudaSuccess ? cudaEventRecord(ev_a[i], sin) : ce;
+    };
+    auto copy_b = [&](int j) -> cudaError_t {                  // columns [j*NP, ..) of op(B)
+      const int c0 = j * NP, nc = (n - c0 < NP) ? (n - c0) : NP;
+      cudaError_t ce;
+      if (tb == 111) ce = cudaMemcpy2DAsync(dB + (size_t)c0 * lddb, (size_t)lddb * sizeof(T), B + (size_t)c0 * ldb, (size_t)ldb * sizeof(T), (size_t)k * sizeof(T), (size_t)nc, cudaMemcpyHostToDevice, sin);
+      else ce = cudaMemcpy2DAsync(dB + c0, (size_t)lddb * sizeof(T), B + c0, (size_t)ldb * sizeof(T), (size_t)nc * sizeof(T), (size_t)k, cudaMemcpyHostToDevice, sin);
+      return ce == cudaSuccess ? cudaEventRecord(ev_b[j], sin) : ce;
+    };
+    PL_CUDA(copy_a(0));
+    PL_CUDA(copy_b(0));
+    for (int j = 1; j < npanels; j++) PL_CUDA(copy_b(j));
+    for (int i = 1; i < nblocks; i++) PL_CUDA(copy_a(i));
+    for (int i = 0; i < nblocks; i++) {
+      const int r0 = i * MB, mr = (m - r0 < MB) ? (m - r0) : MB;
+      PL_CUDA(cudaStreamWaitEvent(s, ev_a[i], 0));
+      for (int j = 0; j < npanels; j++) {
+        const int c0 = j * NP, nc = (n - c0 < NP) ? (n - c0) : NP;
+        if (i == 0) PL_CUDA(cudaStreamWaitEvent(s, ev_b[j], 0));
+        const T *pa = (ta == 111) ? dA + r0 : dA + (size_t)r0 * ldda;
+        const T *pb = (tb == 111) ? dB + (size_t)c0 * lddb : dB + c0;
+        T *pc = dC + r0 + (size_t)c0 * lddc;
+        rc = gemm_device<T>(ta, tb, mr, nc, k, alpha, pa, ldda, pb, lddb, beta, pc, lddc, s, 0);
+        if (rc) goto done;
+        PL_CUDA(cudaEventRecord(ev_tile, s));
+        PL_CUDA(cudaStreamWaitEvent(sout, ev_tile, 0));
+        PL_CUDA(cudaMemcpy2DAsync(C + r0 + (size_t)c0 * ldc, (size_t)ldc * sizeof(T), pc, (size_t)lddc * sizeof(T),
+                                  (size_t)mr * sizeof(T), (size_t)nc, cudaMemcpyDeviceToHost, sout));
+      }
     }
-    PL_CUDA(cudaEventRecord(ev_in[b], sin));
-    PL_CUDA(cudaStreamWaitEvent(s, ev_in[b], 0));
-    if (p >= 2) PL_CUDA(cudaStreamWaitEvent(s, ev_out[b], 0));       // C buffer b drained to the host
-    rc = gemm_device<T>(ta, tb, m, nb, k, alpha, dA, ldda, dB[b], lddb, beta, dC[b], lddc, s, 0);
-    if (rc) goto done;
-    PL_CUDA(cudaEventRecord(ev_done[b], s));
-    PL_CUDA(cudaStreamWaitEvent(sout, ev_done[b], 0));
-    PL_CUDA(cudaMemcpy2DAsync(C + (size_t)j0 * ldc, (size_t)ldc * sizeof(T), dC[b], (size_t)lddc * sizeof(T),
-                              (size_t)m * sizeof(T), (size_t)nb, cudaMemcpyDeviceToHost, sout));
-    PL_CUDA(cudaEventRecord(ev_out[b], sout));
   }
   PL_CUDA(cudaStreamSynchronize(sout));
   PL_CUDA(cudaStreamSynchronize(s));
 done:
 #undef PL_CUDA
-  cudaStreamSynchronize(sin); cudaStreamSynchronize(sout); cudaStreamSynchronize(s);
-  for (int i = 0; i < 2; i++) {
-    if (dB[i]) cudaFree(dB[i]);
-    if (dC[i]) cudaFree(dC[i]);
-    if (ev_in[i]) cudaEventDestroy(ev_in[i]);
-    if (ev_done[i]) cudaEventDestroy(ev_done[i]);
-    if (ev_out[i]) cudaEventDestroy(ev_out[i]);
-  }
+  if (sin) cudaStreamSynchronize(sin);
+  if (sout) cudaStreamSynchronize(sout);
+  cudaStreamSynchronize(s);
+  if (ev_a) { for (int i = 0; i < nblocks; i++) if (ev_a[i]) cudaEventDestroy(ev_a[i]); delete[] ev_a; }
+  if (ev_b) { for (int j = 0; j < npanels; j++) if (ev_b[j]) cudaEventDestroy(ev_b[j]); delete[] ev_b; }
   if (ev_start) cudaEventDestroy(ev_start);
-  if (dA) cudaFree(dA);
-  cudaStreamDestroy(sin); cudaStreamDestroy(sout);
+  if (ev_tile) cudaEventDestroy(ev_tile);
+  ws_free(dC, s); ws_free(dB, s); ws_free(dA, s);
+  if (sin) cudaStreamDestroy(sin);
+  if (sout) cudaStreamDestroy(sout);
   return rc;
 }
 

@@ -60,20 +60,28 @@ class ProcessGrid:
 
 def gemm_plan(n: int, pr: int, pc: int, row: int, col: int, chunks: int = 16):
     """Static description of rank (row,col)'s share of C = A*B (all sizes in elements).
-    K is cut into `chunks` panels of width w (a divisor of both owners' K blocks); panel t of A lives on process
-    column (t*w)//kc and panel t of B on process row (t*w)//kr.  Each panel is one broadcast and one local GEMM,
+    K is cut into panels that never straddle an owner's K block; panel [k0,k1) of A lives on process column k0//kc
+    and of B on process row k0//kr.  Each panel is one broadcast and one local GEMM,
     so only the first panel's transfer is exposed; everything else hides under the DMMA GEMMs."""
     assert n % pr == 0 and n % pc == 0, "N must divide the process grid"
     mb, nb, kr, kc = n // pr, n // pc, n // pr, n // pc
-    nt = max(chunks, pr, pc)
-    while n % nt or kr % (n // nt) or kc % (n // nt):
-        nt += 1
-    w = n // nt
-    panels = []
-    for t in range(nt):
-        k0 = t * w
-        panels.append({"t": t, "k0": k0, "k1": k0 + w, "a_src": row * pc + k0 // kc, "b_src": (k0 // kr) * pc + col,
+    # panels may not straddle an ownership boundary (multiples of kr for B, of kc for A).  The first ownership
+    # granule is cut geometrically (g/8, g/8, g/4, g/2) so the exposed first transfer is small; the rest are whole
+    # granules, which keeps the local GEMMs long (few C read-modify-write sweeps, few partial waves).
+    g = min(kr, kc)
+    assert kr % g == 0 and kc % g == 0
+    widths = []
+    if chunks > 1 and pr * pc > 1 and g % 8 == 0:
+        widths += [g // 8, g // 8, g // 4, g // 2]
+    else:
+        widths += [g]
+    widths += [g] * (n // g - 1)
+    panels, k0 = [], 0
+    for t, w in enumerate(widths):
+        panels.append({"t": t, "k0": k0, "k1": k0 + w, "w": w, "a_src": row * pc + k0 // kc, "b_src": (k0 // kr) * pc + col,
                        "a_mine": k0 // kc == col, "b_mine": k0 // kr == row, "beta": 0.0 if t == 0 else 1.0})
+        k0 += w
+    w = g
     return {"mb": mb, "nb": nb, "kr": kr, "kc": kc, "w": w, "row0": row * mb, "col0": col * nb, "panels": panels,
             "gemms": panels}
 
@@ -116,20 +124,20 @@ class ShardedGemm:
         # slice), B as one w x nb buffer per K panel (ld = w)
         self.A_row = torch.empty(mb * n, dtype=f64, device=dev)
         self.a_panels = [self.A_row[p["k0"] * mb:p["k1"] * mb] for p in P["panels"]]
-        self.b_panels = [torch.empty(w * nb, dtype=f64, device=dev) for _ in P["panels"]]
+        self.b_panels = [torch.empty(p["w"] * nb, dtype=f64, device=dev) for p in P["panels"]]
         self.C = torch.empty(mb * nb, dtype=f64, device=dev)
         # generate only the panels this rank OWNS; the rest arrives by broadcast
         for p in P["panels"]:
             if p["a_mine"]:
-                check(lib.jb_dfill_uniform(self.a_panels[p["t"]].data_ptr(), mb, mb, w, P["row0"], p["k0"], seed, 0, 0.0), "fill A")
+                check(lib.jb_dfill_uniform(self.a_panels[p["t"]].data_ptr(), mb, mb, p["w"], P["row0"], p["k0"], seed, 0, 0.0), "fill A")
             if p["b_mine"]:
-                check(lib.jb_dfill_uniform(self.b_panels[p["t"]].data_ptr(), w, w, nb, p["k0"], P["col0"], seed + 1, 0, 0.0), "fill B")
+                check(lib.jb_dfill_uniform(self.b_panels[p["t"]].data_ptr(), p["w"], p["w"], nb, p["k0"], P["col0"], seed + 1, 0, 0.0), "fill B")
         torch.cuda.synchronize()
 
     def _local_gemm(self, p):
         P, lib = self.plan, self.lib
-        lib.cblas_dgemm(102, 111, 111, P["mb"], P["nb"], P["w"], 1.0, self.a_panels[p["t"]].data_ptr(), P["mb"],
-                        self.b_panels[p["t"]].data_ptr(), P["w"], p["beta"], self.C.data_ptr(), P["mb"])
+        lib.cblas_dgemm(102, 111, 111, P["mb"], P["nb"], p["w"], 1.0, self.a_panels[p["t"]].data_ptr(), P["mb"],
+                        self.b_panels[p["t"]].data_ptr(), p["w"], p["beta"], self.C.data_ptr(), P["mb"])
 
     def step(self):
         P, grid = self.plan, self.grid

@@ -53,21 +53,21 @@ def _worker(rank, world, port, n, q):
     try:
         grid = ProcessGrid(world, rank, dist)
         P = gemm_plan(n, grid.pr, grid.pc, grid.row, grid.col, chunks=6)
-        mb, nb, w = P["mb"], P["nb"], P["w"]
+        mb, nb = P["mb"], P["nb"]
         # column-major panels as flat tensors; only the owned panels are filled
-        a_panels = [torch.zeros(mb * w, dtype=torch.float64) for _ in P["panels"]]
-        b_panels = [torch.zeros(w * nb, dtype=torch.float64) for _ in P["panels"]]
+        a_panels = [torch.zeros(mb * p["w"], dtype=torch.float64) for p in P["panels"]]
+        b_panels = [torch.zeros(p["w"] * nb, dtype=torch.float64) for p in P["panels"]]
         for p in P["panels"]:
             if p["a_mine"]:
-                a_panels[p["t"]].copy_(torch.from_numpy(synth.uniform(mb, w, 7, "d", P["row0"], p["k0"]).T.copy().ravel()))
+                a_panels[p["t"]].copy_(torch.from_numpy(synth.uniform(mb, p["w"], 7, "d", P["row0"], p["k0"]).T.copy().ravel()))
             if p["b_mine"]:
-                b_panels[p["t"]].copy_(torch.from_numpy(synth.uniform(w, nb, 8, "d", p["k0"], P["col0"]).T.copy().ravel()))
+                b_panels[p["t"]].copy_(torch.from_numpy(synth.uniform(p["w"], nb, 8, "d", p["k0"], P["col0"]).T.copy().ravel()))
         Cacc = np.zeros((mb, nb))
 
         def local_gemm(p):
             nonlocal Cacc
-            Ap = a_panels[p["t"]].numpy().reshape(w, mb).T      # mb x w
-            Bp = b_panels[p["t"]].numpy().reshape(nb, w).T      # w x nb
+            Ap = a_panels[p["t"]].numpy().reshape(p["w"], mb).T      # mb x w
+            Bp = b_panels[p["t"]].numpy().reshape(nb, p["w"]).T      # w x nb
             Cacc = p["beta"] * Cacc + Ap @ Bp
 
         summa_step(P, grid, a_panels, b_panels, local_gemm)
@@ -84,7 +84,7 @@ def test_summa_schedule_gloo(world):
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, 48, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 64, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=180) for _ in range(world)]

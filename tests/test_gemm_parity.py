@@ -199,3 +199,26 @@ def test_sgemm_ragged_large(gpu, blas, rng, ta, tb):
     assert_close("s", k, Cg, Cr, A, B)
     Cg, Cr, A, B, *_ = run_both(gpu, blas, "s", ta, tb, 256, 384, 128, 1.0, 0.0, rng)
     assert_close("s", 128, Cg, Cr, A, B)
+
+
+@pytest.mark.parametrize("ta,tb,beta", [(111, 111, 0.0), (112, 112, 0.5)])
+def test_host_pipelined_large(gpu, gpu_host, rng, ta, tb, beta):
+    """All-host operands above the pipelining threshold: row blocks of A / column panels of B stream through the
+    GPU (gemm_host_pipelined).  Checked against the device-resident path on the same data."""
+    m, n, k = 8192 + 64, 2304, 2816
+    ra, ca = (m, k) if ta == 111 else (k, m)
+    rb, cb = (k, n) if tb == 111 else (n, k)
+    A = rand(rng, "d", ra, ca, ra + 2); B = rand(rng, "d", rb, cb, rb + 4); C0 = rand(rng, "d", m, n, m + 2)
+    if beta == 0.0:
+        C0[:m, :] = np.nan
+    C1, C2 = C0.copy(order="F"), C0.copy(order="F")
+    gpu_host.gemm("d", 102, ta, tb, m, n, k, 1.25, A, ra + 2, B, rb + 4, beta, C1, m + 2)
+    gpu.gemm("d", 102, ta, tb, m, n, k, 1.25, A, ra + 2, B, rb + 4, beta, C2, m + 2)
+    assert np.isfinite(C1[:m]).all() and np.isnan(C1[m:]).all()
+    assert fro(C1[:m] - C2[:m]) / fro(C2[:m]) <= 4 * k * EPS["d"]
+    # spot check a few entries against a float64 dot product
+    for (i, j) in ((0, 0), (m - 1, n - 1), (4100, 1234)):
+        a = A[i, :k] if ta == 111 else A[:k, i]
+        b = B[:k, j] if tb == 111 else B[j, :k]
+        want = 1.25 * float(np.dot(a, b)) + (beta * C0[i, j] if beta else 0.0)
+        assert abs(C1[i, j] - want) <= 1e-9 * k
