@@ -7,6 +7,8 @@
 // kernel, the block row is solved against the unit-lower diagonal block, and the trailing
 // matrix is updated by this library's own GEMM (gemm_device: DMMA for double).
 #include "jb_common.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 namespace jb {
 
@@ -99,14 +101,138 @@ lu_panel_kernel(int pm, int jb, T *__restrict__ Pg, int ldg, int *__restrict__ i
   }
 }
 
+// ------------------------------------------------------------------ LU panel, many CTAs (tall panels)
+// Same algorithm and arithmetic as lu_panel_kernel, but the pm rows are split over a cooperative grid: each
+// CTA keeps its slab of the panel in shared memory, and per column there is exactly ONE grid-wide barrier.
+// Before the barrier every CTA publishes its best pivot candidate together with that row's panel entries (and
+// the owner of the diagonal row publishes that row), so after the barrier every CTA can pick the global pivot
+// (max magnitude, lowest row wins ties), fetch the pivot row, perform its share of the interchange and update
+// its own rows without further communication.  Scratch is double buffered by column parity.
+struct PanelScratch {
+  // all arrays have a leading [2] parity dimension
+  double *cand_val;   // [2][G]   magnitude of the CTA's candidate (-1: none)
+  int *cand_row;      // [2][G]   its panel row index
+  void *cand_data;    // [2][G][NB] that row's panel entries
+  void *diag_data;    // [2][NB]  entries of panel row c (the row being swapped down)
+};
+
+// scratch written by other CTAs is read through the L2 (never a possibly stale L1 line)
+template <typename T> __device__ __forceinline__ T ld_cg(const T *p) {
+  if constexpr (sizeof(T) == 4) { float v = __ldcg(reinterpret_cast<const float *>(p)); return *reinterpret_cast<T *>(&v); }
+  else if constexpr (sizeof(T) == 8) { double v = __ldcg(reinterpret_cast<const double *>(p)); return *reinterpret_cast<T *>(&v); }
+  else { double2 v = __ldcg(reinterpret_cast<const double2 *>(p)); return *reinterpret_cast<T *>(&v); }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+lu_panel_coop_kernel(int pm, int jb, T *__restrict__ Pg, int ldg, int *__restrict__ ipiv, int *info, int row_off,
+                     int rows_per_cta, PanelScratch sc) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using R = typename Num<T>::R;
+  T *S = reinterpret_cast<T *>(smem_raw);                 // [jb][lds] column-major slab
+  __shared__ R red_val[8];
+  __shared__ int red_idx[8];
+  __shared__ T s_u[NB];
+  __shared__ int s_piv, s_win;
+  const int tid = threadIdx.x, nt = blockDim.x, G = gridDim.x, cta = blockIdx.x;
+  const int r_lo = cta * rows_per_cta, r_hi = min(pm, r_lo + rows_per_cta), nr = max(r_hi - r_lo, 0);
+  const int lds = rows_per_cta | 1;
+  for (int c = 0; c < jb; c++)
+    for (int r = tid; r < nr; r += nt) S[r + (size_t)c * lds] = Pg[(r_lo + r) + (size_t)c * ldg];
+  __syncthreads();
+  T *cand_data = reinterpret_cast<T *>(sc.cand_data);
+  T *diag_data = reinterpret_cast<T *>(sc.diag_data);
+  const int ncols = min(jb, pm);
+  for (int c = 0; c < ncols; c++) {
+    const int par = c & 1;
+    // ---- local candidate among my rows >= c
+    R best = (R)-1; int bi = 0x7fffffff;
+    for (int r = max(c - r_lo, 0) + tid; r < nr; r += nt) {
+      R v = Num<T>::abs1(S[r + (size_t)c * lds]);
+      if (v > best) { best = v; bi = r_lo + r; }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+      R ov = __shfl_down_sync(0xffffffffu, best, off);
+      int oi = __shfl_down_sync(0xffffffffu, bi, off);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if ((tid & 31) == 0) { red_val[tid >> 5] = best; red_idx[tid >> 5] = bi; }
+    __syncthreads();
+    if (tid < 32) {
+      const int nw = nt >> 5;
+      best = tid < nw ? red_val[tid] : (R)-1;
+      bi = tid < nw ? red_idx[tid] : 0x7fffffff;
+      for (int off = 16; off > 0; off >>= 1) {
+        R ov = __shfl_down_sync(0xffffffffu, best, off);
+        int oi = __shfl_down_sync(0xffffffffu, bi, off);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+      }
+      if (tid == 0) {
+        // a slab that holds row c but only NaNs/none better keeps row c as its candidate (i?amax semantics)
+        if (bi == 0x7fffffff && c >= r_lo && c < r_hi) { bi = c; best = (R)-0.5; }
+        s_piv = bi;
+        sc.cand_val[par * G + cta] = (double)best;
+        sc.cand_row[par * G + cta] = bi;
+      }
+    }
+    __syncthreads();
+    const int my_cand = s_piv;
+    if (tid < jb) {
+      if (my_cand != 0x7fffffff) cand_data[((size_t)par * G + cta) * NB + tid] = S[(my_cand - r_lo) + (size_t)tid * lds];
+      if (c >= r_lo && c < r_hi) diag_data[par * NB + tid] = S[(c - r_lo) + (size_t)tid * lds];
+    }
+    __threadfence();
+    grid.sync();
+    // ---- global pivot: every CTA reduces the G candidates identically
+    if (tid < 32) {
+      double bv = -1.0; int br = 0x7fffffff, bw = 0;
+      for (int g = tid; g < G; g += 32) {
+        double v = __ldcg(&sc.cand_val[par * G + g]); int rr = __ldcg(&sc.cand_row[par * G + g]);
+        if (rr != 0x7fffffff && (v > bv || (v == bv && rr < br))) { bv = v; br = rr; bw = g; }
+      }
+      for (int off = 16; off > 0; off >>= 1) {
+        double ov = __shfl_down_sync(0xffffffffu, bv, off);
+        int orr = __shfl_down_sync(0xffffffffu, br, off), ow = __shfl_down_sync(0xffffffffu, bw, off);
+        if (orr != 0x7fffffff && (ov > bv || (ov == bv && orr < br))) { bv = ov; br = orr; bw = ow; }
+      }
+      if (tid == 0) { s_piv = br; s_win = bw; }
+    }
+    __syncthreads();
+    const int p = s_piv, win = s_win;
+    if (tid < jb) s_u[tid] = ld_cg<T>(&cand_data[((size_t)par * G + win) * NB + tid]);
+    if (cta == 0 && tid == 0) ipiv[c] = p + row_off + 1;
+    __syncthreads();
+    // ---- my share of the interchange (row c <- pivot row, row p <- old row c)
+    if (p != c && tid < jb) {
+      if (p >= r_lo && p < r_hi) S[(p - r_lo) + (size_t)tid * lds] = ld_cg<T>(&diag_data[par * NB + tid]);
+      if (c >= r_lo && c < r_hi) S[(c - r_lo) + (size_t)tid * lds] = s_u[tid];
+    }
+    __syncthreads();
+    const T piv = s_u[c];
+    const bool zero = Num<T>::is_zero(piv);
+    if (zero && cta == 0 && tid == 0 && *info == 0) *info = c + row_off + 1;
+    const T rinv = zero ? Num<T>::zero() : Num<T>::recip(piv);
+    for (int r = max(c + 1 - r_lo, 0) + tid; r < nr; r += nt) {
+      T l = S[r + (size_t)c * lds];
+      if (!zero) { l = Num<T>::cmul(l, rinv); S[r + (size_t)c * lds] = l; }
+      for (int cc = c + 1; cc < jb; cc++) S[r + (size_t)cc * lds] = Num<T>::msub(S[r + (size_t)cc * lds], l, s_u[cc]);
+    }
+    __syncthreads();
+  }
+  for (int c = 0; c < jb; c++)
+    for (int r = tid; r < nr; r += nt) Pg[(r_lo + r) + (size_t)c * ldg] = S[r + (size_t)c * lds];
+}
+
 // Applies interchanges ipiv[k0..k1) (1-based global rows) to columns [c0,c1) of A, forward.
 template <typename T>
-__global__ void laswp_kernel(T *__restrict__ A, int lda, int c0, int c1, const int *__restrict__ ipiv, int k0, int k1) {
+__global__ void laswp_kernel(T *__restrict__ A, int lda, int c0, int c1, const int *__restrict__ ipiv, int k0, int k1,
+                             int row_base) {
   int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= c1) return;
   T *col = A + (size_t)c * lda;
   for (int k = k0; k < k1; k++) {
-    int p = ipiv[k] - 1;
+    int p = ipiv[k] - 1 - row_base;   // ipiv holds rows of the whole matrix; A points at its row `row_base`
     if (p != k) { T t = col[k]; col[k] = col[p]; col[p] = t; }
   }
 }
@@ -283,32 +409,47 @@ __global__ void permute_rows_kernel(int inverse, int n, int nrhs, const int *__r
 }
 
 // ------------------------------------------------------------------ host-side drivers
+// One level of the right-looking LU with NB = 32 panels on the m x n block at A, whose first row is row
+// `row_base` of the caller's matrix (ipiv / info are written in the caller's numbering; d_ipiv is indexed locally).
 template <typename T>
-int getrf_device(int m, int n, T *A, int lda, int *d_ipiv, int *d_info, cudaStream_t s) {
+static int getrf_nb32(int m, int n, T *A, int lda, int *d_ipiv, int *d_info, int row_base, PanelScratch sc, bool have_scratch,
+                      int coop_min_rows, cudaStream_t s) {
   const int mn = m < n ? m : n;
-  if (mn <= 0) return 0;
   const size_t smem_cap = 200 * 1024;
-  JB_CUDA(cudaFuncSetAttribute(lu_panel_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+  const int nsm = num_sms();
   for (int j0 = 0; j0 < mn; j0 += NB) {
     const int jb = (mn - j0 < NB) ? (mn - j0) : NB;
     const int pm = m - j0;
-    size_t need = (size_t)(pm | 1) * jb * sizeof(T);
-    int use_smem = need <= smem_cap;
-    int threads = pm >= PANEL_THREADS ? PANEL_THREADS : ((pm + 31) / 32) * 32;
-    if (threads < 64) threads = 64;
-    lu_panel_kernel<T><<<1, threads, use_smem ? need : 0, s>>>(pm, jb, A + j0 + (size_t)j0 * lda, lda, d_ipiv + j0, d_info,
-                                                              j0, use_smem);
-    count_launch();
-    // panel ipiv holds global row numbers; interchange the columns left and right of the panel
+    if (have_scratch && pm >= coop_min_rows) {
+      int rows_per_cta = 128;
+      int G = (pm + rows_per_cta - 1) / rows_per_cta;
+      if (G > nsm) { G = nsm; rows_per_cta = ((pm + G - 1) / G + 31) / 32 * 32; G = (pm + rows_per_cta - 1) / rows_per_cta; }
+      size_t shm = (size_t)(rows_per_cta | 1) * jb * sizeof(T);
+      T *Pp = A + j0 + (size_t)j0 * lda;
+      int *pv = d_ipiv + j0;
+      int ldp = lda, roff = row_base + j0, jbb = jb, pmm = pm;
+      void *args[] = {&pmm, &jbb, &Pp, &ldp, &pv, &d_info, &roff, &rows_per_cta, &sc};
+      JB_CUDA(cudaLaunchCooperativeKernel((void *)lu_panel_coop_kernel<T>, dim3(G), dim3(256), args, shm, s));
+      count_launch();
+    } else {
+      size_t need = (size_t)(pm | 1) * jb * sizeof(T);
+      int use_smem = need <= smem_cap;
+      int threads = pm >= PANEL_THREADS ? PANEL_THREADS : ((pm + 31) / 32) * 32;
+      if (threads < 64) threads = 64;
+      lu_panel_kernel<T><<<1, threads, use_smem ? need : 0, s>>>(pm, jb, A + j0 + (size_t)j0 * lda, lda, d_ipiv + j0, d_info,
+                                                                row_base + j0, use_smem);
+      count_launch();
+    }
+    // interchange the columns of this block left and right of the panel
     if (j0 > 0) {
-      laswp_kernel<T><<<(j0 + 127) / 128, 128, 0, s>>>(A, lda, 0, j0, d_ipiv, j0, j0 + jb);
+      laswp_kernel<T><<<(j0 + 127) / 128, 128, 0, s>>>(A, lda, 0, j0, d_ipiv, j0, j0 + jb, row_base);
       count_launch();
     }
     const int nr = n - j0 - jb;
     if (nr > 0) {
-      laswp_kernel<T><<<(nr + 127) / 128, 128, 0, s>>>(A, lda, j0 + jb, n, d_ipiv, j0, j0 + jb);
+      laswp_kernel<T><<<(nr + 127) / 128, 128, 0, s>>>(A, lda, j0 + jb, n, d_ipiv, j0, j0 + jb, row_base);
       count_launch();
-      int blocks = (nr + 7) / 8; if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
+      int blocks = (nr + 7) / 8; if (blocks > 4 * nsm) blocks = 4 * nsm;
       trsm_small_left_kernel<T><<<blocks, 256, 0, s>>>(1, 1, 111, jb, nr, A + j0 + (size_t)j0 * lda, lda,
                                                        A + j0 + (size_t)(j0 + jb) * lda, lda, nullptr);
       count_launch();
@@ -321,6 +462,67 @@ int getrf_device(int m, int n, T *A, int lda, int *d_ipiv, int *d_info, cudaStre
       }
     }
   }
+  return 0;
+}
+
+template <typename T>
+static int trsm_left_blocked(int stored_lower, int trans, int unit, int n, int nrhs, const T *A, int lda, T *B, int ldb,
+                             cudaStream_t s);
+
+// Two-level right-looking LU: outer panels of NB2 columns are factorised by the NB=32 routine (tall panels on the
+// cooperative multi-CTA kernel); the interchanges, the unit-lower block-row solve and ONE rank-NB2 GEMM update per
+// outer step then touch the rest of the matrix — NB2/32 times fewer sweeps over the trailing matrix.
+template <typename T>
+int getrf_device(int m, int n, T *A, int lda, int *d_ipiv, int *d_info, cudaStream_t s) {
+  const int mn = m < n ? m : n;
+  if (mn <= 0) return 0;
+  const size_t smem_cap = 200 * 1024;
+  JB_CUDA(cudaFuncSetAttribute(lu_panel_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+  const int coop_min_rows = option("getrf.coop_min_rows") > 0 ? option("getrf.coop_min_rows") : 1024;
+  const int nsm = num_sms();
+  unsigned char *scratch = nullptr;
+  PanelScratch sc{};
+  if (m >= coop_min_rows) {
+    const size_t per = 2 * ((size_t)nsm * (sizeof(double) + sizeof(int) + NB * sizeof(T)) + NB * sizeof(T)) + 256;
+    if (int rc = ws_alloc((void **)&scratch, per, s)) return rc;
+    unsigned char *q = scratch;
+    sc.cand_val = (double *)q; q += 2 * (size_t)nsm * sizeof(double);
+    sc.cand_row = (int *)q; q += 2 * (size_t)nsm * sizeof(int);
+    q = (unsigned char *)(((uintptr_t)q + 15) & ~(uintptr_t)15);
+    sc.cand_data = q; q += 2 * (size_t)nsm * NB * sizeof(T);
+    sc.diag_data = q;
+    JB_CUDA(cudaFuncSetAttribute(lu_panel_coop_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+  }
+  int NB2 = option("getrf.nb2");
+  if (NB2 <= 0) NB2 = (mn >= 4096) ? 256 : mn;
+  int rc = 0;
+  if (mn <= NB2 + NB) {
+    rc = getrf_nb32<T>(m, n, A, lda, d_ipiv, d_info, 0, sc, scratch != nullptr, coop_min_rows, s);
+  } else {
+    const T minus1 = Num<T>::neg(Num<T>::one()), one = Num<T>::one();
+    for (int J0 = 0; J0 < mn && !rc; J0 += NB2) {
+      const int jb2 = (mn - J0 < NB2) ? (mn - J0) : NB2;
+      rc = getrf_nb32<T>(m - J0, jb2, A + J0 + (size_t)J0 * lda, lda, d_ipiv + J0, d_info, J0, sc, scratch != nullptr,
+                         coop_min_rows, s);
+      if (rc) break;
+      if (J0 > 0) {
+        laswp_kernel<T><<<(J0 + 127) / 128, 128, 0, s>>>(A, lda, 0, J0, d_ipiv, J0, J0 + jb2, 0);
+        count_launch();
+      }
+      const int nr = n - J0 - jb2;
+      if (nr > 0) {
+        laswp_kernel<T><<<(nr + 127) / 128, 128, 0, s>>>(A, lda, J0 + jb2, n, d_ipiv, J0, J0 + jb2, 0);
+        count_launch();
+        rc = trsm_left_blocked<T>(1, 111, 1, jb2, nr, A + J0 + (size_t)J0 * lda, lda, A + J0 + (size_t)(J0 + jb2) * lda, lda, s);
+        const int mr = m - J0 - jb2;
+        if (!rc && mr > 0)
+          rc = gemm_device<T>(111, 111, mr, nr, jb2, minus1, A + (J0 + jb2) + (size_t)J0 * lda, lda,
+                              A + J0 + (size_t)(J0 + jb2) * lda, lda, one, A + (J0 + jb2) + (size_t)(J0 + jb2) * lda, lda, s, 0);
+      }
+    }
+  }
+  ws_free(scratch, s);
+  if (rc) return rc;
   JB_CUDA(cudaGetLastError());
   return 0;
 }

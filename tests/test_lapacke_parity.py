@@ -253,3 +253,80 @@ def test_potrf_two_level(gpu, blas, rng, t, uplo):
     assert fro(rec - S) / (n * EPS[t] * fro(S)) <= 10
     Sbad2 = S.copy(order="F"); Sbad2[450, 450] = -5.0
     assert blas.potrf(t, 102, uplo, n, Sbad2, n) == 451
+
+
+@pytest.mark.parametrize("t", TYPES)
+@pytest.mark.parametrize("shape", [(300, 300), (513, 200), (200, 513), (1500, 1500)])
+def test_getrf_cooperative_panel(gpu, blas, rng, t, shape):
+    """Tall panels run on the cooperative multi-CTA panel kernel (one grid barrier per column); forced on at
+    small sizes through the option, natural at 1500.  Pivots must equal OpenBLAS's, residual within bound."""
+    from jalla_b200._lib import lib
+    m, n = shape
+    if t in "cz" and m == 1500:
+        m = n = 1100
+    A = rand(rng, t, m, n, m + 1)
+    A[:m, :] += 0.01 * np.arange(m * n).reshape(m, n).astype(NP[t]) / (m * n)     # breaks exact ties
+    Ag, Ab = A.copy(order="F"), A.copy(order="F")
+    pg, pb = np.zeros(min(m, n), np.int32), np.zeros(min(m, n), np.int32)
+    lib.jb_set_option(b"getrf.coop_min_rows", 64)
+    try:
+        assert gpu.getrf(t, 102, m, n, Ag, m + 1, pg) == 0
+    finally:
+        lib.jb_set_option(b"getrf.coop_min_rows", 0)
+    assert blas.getrf(t, 102, m, n, Ab, m + 1, pb) == 0
+    if no_near_ties(None, t, A[:m, :], thresh=1e-5 if t in "sc" else 1e-9):
+        np.testing.assert_array_equal(pg, pb)
+    assert lu_residual(t, A[:m, :], Ag[:m, :], pg) <= 10
+    # singular column and ties behave like the single-CTA kernel
+    if t == "d" and m == 300:
+        Z = rand(rng, t, m, n); Z[:, 40] = 0
+        Zg, Zb = Z.copy(order="F"), Z.copy(order="F")
+        lib.jb_set_option(b"getrf.coop_min_rows", 64)
+        try:
+            ig = gpu.getrf(t, 102, m, n, Zg, m, pg)
+        finally:
+            lib.jb_set_option(b"getrf.coop_min_rows", 0)
+        assert ig == blas.getrf(t, 102, m, n, Zb, m, pb) == 41
+        np.testing.assert_array_equal(pg, pb)
+        I = np.asfortranarray(rng.integers(-2, 3, (m, n)).astype(np.float64) + 4 * np.eye(m))
+        Ig, Ib = I.copy(order="F"), I.copy(order="F")
+        lib.jb_set_option(b"getrf.coop_min_rows", 64)
+        try:
+            ig = gpu.getrf(t, 102, m, n, Ig, m, pg)
+        finally:
+            lib.jb_set_option(b"getrf.coop_min_rows", 0)
+        assert ig == blas.getrf(t, 102, m, n, Ib, m, pb)
+        np.testing.assert_array_equal(pg[:32], pb[:32])   # first panel: identical arithmetic, exact ties -> lowest index
+
+
+@pytest.mark.parametrize("t", TYPES)
+def test_getrf_two_level(gpu, blas, rng, t):
+    """Outer panels of NB2 columns (forced to 64 here) factorised by the NB=32 level, then one rank-NB2 update."""
+    from jalla_b200._lib import lib
+    for (m, n) in ((333, 333), (400, 250), (250, 400)):
+        A = rand(rng, t, m, n, m + 2)
+        Ag, Ab = A.copy(order="F"), A.copy(order="F")
+        pg, pb = np.zeros(min(m, n), np.int32), np.zeros(min(m, n), np.int32)
+        lib.jb_set_option(b"getrf.nb2", 64); lib.jb_set_option(b"getrf.coop_min_rows", 128)
+        try:
+            assert gpu.getrf(t, 102, m, n, Ag, m + 2, pg) == 0
+        finally:
+            lib.jb_set_option(b"getrf.nb2", 0); lib.jb_set_option(b"getrf.coop_min_rows", 0)
+        assert blas.getrf(t, 102, m, n, Ab, m + 2, pb) == 0
+        if no_near_ties(None, t, A[:m, :], thresh=1e-4 if t in "sc" else 1e-9):
+            np.testing.assert_array_equal(pg, pb)
+        assert lu_residual(t, A[:m, :], Ag[:m, :], pg) <= 10
+        assert np.isnan(Ag[m:, :]).all()
+
+
+def test_dgesv_large_natural_path(gpu, blas, rng):
+    """n = 4200: the default configuration takes the two-level + cooperative-panel path."""
+    n = 4200
+    A = rand(rng, "d", n, n); B = rand(rng, "d", n, 2)
+    Ag, Ab, Bg, Bb = A.copy(order="F"), A.copy(order="F"), B.copy(order="F"), B.copy(order="F")
+    pg, pb = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    assert gpu.gesv("d", 102, n, 2, Ag, n, pg, Bg, n) == 0
+    assert blas.gesv("d", 102, n, 2, Ab, n, pb, Bb, n) == 0
+    np.testing.assert_array_equal(pg, pb)
+    assert fro(A @ Bg - B) / (fro(A) * fro(Bg) * n * EPS["d"]) <= 10
+    assert fro(Ag - Ab) / fro(Ab) <= 1e3 * n * EPS["d"]
