@@ -269,7 +269,9 @@ def main():
                        "n": N, "grid": f"{grid.pr}x{grid.pc}", "l2": "operands 2 GiB each >> 126 MB L2, no flush needed",
                        "inputs": "counter-based U(-1,1) keyed on global (i,j), generated on device"},
             "roofline": {"bound": "tensor", "achieved": ach, "peak": DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
-                         "frac": ach / DMMA_PEAK_TFLOPS, "traffic": None,
+                         "frac": ach / DMMA_PEAK_TFLOPS,
+                         # dram__bytes_read+write of one N=16384 launch (profiles/ncu_dgemm_r1a.txt); only meaningful at N=1
+                         "traffic": 86.117e9 if world == 1 else None,
                          "peak_source": "measured FP64 DMMA issue-rate peak (tools/peaks.cu, profiles/peaks_r1.jsonl); "
                                         "MEASURED_PEAKS.json holds no FP64 figure",
                          "kernel": "dgemm_dmma_kernel", "kernel_ms": kern_ms,
@@ -287,7 +289,8 @@ def main():
             "config": {"workload": "configs[2]: 1,000,000 independent 32x32 Double systems, getrf+getrs (jb_dgesv_batched), "
                                    "batch split across ranks, no collective", "flush": "8.4 GB working set >> L2"},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                         "traffic": None, "peak_source": hbm_src, "kernel": "lu32v2_kernel<1,1,20>",
+                         # dram__bytes_read+write of one 10^6-system launch (profiles/ncu_lu32_r1b.txt) = algorithmic bytes
+                         "traffic": 16.98e9 if world == 1 else None, "peak_source": hbm_src, "kernel": "lu32v2_kernel<1,1,20>",
                          "kernel_ms": lu_kern_ms, "algorithmic_bytes_per_launch": per_rank * LU_BYTES_PER_SYSTEM,
                          "frac_of_nominal_8TBs": ach / 8000.0},
         }
