@@ -290,7 +290,7 @@ def main():
                                    "batch split across ranks, no collective", "flush": "8.4 GB working set >> L2"},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                          # dram__bytes_read+write of one 10^6-system launch (profiles/ncu_lu32_r1b.txt) = algorithmic bytes
-                         "traffic": 16.98e9 if world == 1 else None, "peak_source": hbm_src, "kernel": "lu32v2_kernel<1,1,20>",
+                         "traffic": 16.98e9 if world == 1 else None, "peak_source": hbm_src, "kernel": "lu32v2_kernel<1,1,16>",
                          "kernel_ms": lu_kern_ms, "algorithmic_bytes_per_launch": per_rank * LU_BYTES_PER_SYSTEM,
                          "frac_of_nominal_8TBs": ach / 8000.0},
         }
