@@ -63,6 +63,38 @@ class DeviceOps:
     def copy(self, m, n, A, offa, lda, B, offb, ldb):
         self.check(self.lib.jb_dlacpy(111, m, n, self._p(A, offa), lda, self._p(B, offb), ldb), "lacpy")
 
+    # ---- two-stream look-ahead support: "panel" and "update" streams, events between them
+    def make_streams(self):
+        self.s_update = self.torch.cuda.current_stream()
+        self.s_panel = self.torch.cuda.Stream()
+        return True
+
+    def on(self, which):
+        """Context manager: subsequent C-ABI calls, torch ops and NCCL collectives are ordered on that stream."""
+        ops = self
+        st = self.s_panel if which == "panel" else self.s_update
+
+        class _Ctx:
+            def __enter__(self_inner):
+                self_inner.ctx = ops.torch.cuda.stream(st)
+                self_inner.ctx.__enter__()
+                ops.lib.jb_set_stream(__import__("ctypes").c_void_p(st.cuda_stream))
+
+            def __exit__(self_inner, *a):
+                self_inner.ctx.__exit__(*a)
+                ops.lib.jb_set_stream(__import__("ctypes").c_void_p(ops.s_update.cuda_stream))
+        return _Ctx()
+
+    def event(self, which):
+        st = self.s_panel if which == "panel" else self.s_update
+        e = self.torch.cuda.Event()
+        e.record(st)
+        return e
+
+    def wait(self, which, ev):
+        st = self.s_panel if which == "panel" else self.s_update
+        st.wait_event(ev)
+
     def finish(self):
         self.torch.cuda.synchronize()
         self.check_last("dist_chol")
@@ -110,66 +142,124 @@ class DistCholesky:
         if group is not None:
             self.g.dist.broadcast(t, src=src, group=group)
 
-    def potrf(self) -> int:
+    def _buffers(self):
+        """Ping-pong panel buffers (by step parity) so that look-ahead never allocates while another stream reads."""
+        if not hasattr(self, "_W"):
+            nb, ops = self.nb, self.ops
+            self._W = [{"row": ops.empty(max(self.Tr, 1) * nb * nb), "col": ops.empty(max(self.Tc, 1) * nb * nb),
+                        "pack": ops.empty(max(self.Tc, 1) * nb * nb)} for _ in range(2)]
+        return self._W
+
+    def _panel_phase(self, K):
+        """Steps 1-5 of iteration K: factor the diagonal tile, solve the panel below it, and distribute it:
+        Wrow = L_IK for my local tile rows I > K (m1 x nb), Wcol = L_JK for my local tile columns J > K (n1 x nb)."""
         g, nb, ops, T = self.g, self.nb, self.ops, self.T
-        dist = g.dist
-        for K in range(T):
-            kr, kc = K % g.pr, K % g.pc
-            lkr, lk = K // g.pr, K // g.pc
-            owner = kr * g.pc + kc
-            # 1. diagonal tile
-            if g.rank == owner:
-                info = ops.potrf(self.A, self.tile_off(lkr, lk), self.ld, nb)
-                if info and not self.info:
-                    self.info = K * nb + info if info > 0 else info
-                ops.copy(nb, nb, self.A, self.tile_off(lkr, lk), self.ld, self.D, 0, nb)
-            # 2. + 3. process column kc: receive the diagonal factor, solve the panel below it
-            i_start = self.first_row_above(g.row, K)
-            m1 = (self.Tr - i_start) * nb
-            if g.col == kc:
-                if g.pr > 1:
-                    self._bcast(self.D, owner, g.col_group)
-                if m1 > 0:
-                    ops.trsm_right_lt(m1, nb, self.D, 0, nb, self.A, self.tile_off(i_start, lk), self.ld)
-            if K == T - 1:
-                break
-            # 4. row broadcast of the solved panel (packed m1 x nb)
-            Wrow = ops.empty(max(m1, 1) * nb)
-            if g.col == kc and m1 > 0:
-                ops.copy(m1, nb, self.A, self.tile_off(i_start, lk), self.ld, Wrow, 0, m1)
-            if g.pc > 1 and m1 > 0:
-                self._bcast(Wrow, g.row * g.pc + kc, g.row_group)
-            # 5. transpose-role tiles: L_JK for my local tile columns J > K, gathered down my process column
-            j_start = self.first_col_above(g.col, K)
-            n1 = (self.Tc - j_start) * nb
-            Wcol = ops.empty(max(n1, 1) * nb)
-            for rp in range(g.pr):
-                tiles = [J for J in range(K + 1, T) if J % g.pc == g.col and J % g.pr == rp]
-                if not tiles:
-                    continue
-                i_start_rp = self.first_row_above(rp, K)
-                m1_rp = (self.local_rows(rp) - i_start_rp) * nb
-                if g.pr == 1:
-                    for J in tiles:
-                        ops.copy(nb, nb, Wrow, (J // g.pr - i_start_rp) * nb, m1_rp, Wcol, (J // g.pc - j_start) * nb, n1)
-                    continue
-                buf = ops.empty(len(tiles) * nb * nb)
-                ldbuf = len(tiles) * nb
-                if g.row == rp:
-                    for q, J in enumerate(tiles):
-                        ops.copy(nb, nb, Wrow, (J // g.pr - i_start_rp) * nb, m1_rp, buf, q * nb, ldbuf)
-                self._bcast(buf, rp * g.pc + g.col, g.col_group)
+        kr, kc = K % g.pr, K % g.pc
+        lkr, lk = K // g.pr, K // g.pc
+        owner = kr * g.pc + kc
+        W = self._buffers()[K & 1]
+        if g.rank == owner:
+            info = ops.potrf(self.A, self.tile_off(lkr, lk), self.ld, nb)
+            if info and not self.info:
+                self.info = K * nb + info if info > 0 else info
+            ops.copy(nb, nb, self.A, self.tile_off(lkr, lk), self.ld, self.D, 0, nb)
+        i_start = self.first_row_above(g.row, K)
+        m1 = (self.Tr - i_start) * nb
+        if g.col == kc:
+            if g.pr > 1:
+                self._bcast(self.D, owner, g.col_group)
+            if m1 > 0:
+                ops.trsm_right_lt(m1, nb, self.D, 0, nb, self.A, self.tile_off(i_start, lk), self.ld)
+        j_start = self.first_col_above(g.col, K)
+        n1 = (self.Tc - j_start) * nb
+        if K == T - 1:
+            return {"i_start": i_start, "j_start": j_start, "m1": m1, "n1": n1, "row": W["row"], "col": W["col"]}
+        Wrow, Wcol = W["row"], W["col"]
+        if g.col == kc and m1 > 0:
+            ops.copy(m1, nb, self.A, self.tile_off(i_start, lk), self.ld, Wrow, 0, m1)
+        if g.pc > 1 and m1 > 0:
+            self._bcast(Wrow[: m1 * nb], g.row * g.pc + kc, g.row_group)
+        for rp in range(g.pr):
+            tiles = [J for J in range(K + 1, T) if J % g.pc == g.col and J % g.pr == rp]
+            if not tiles:
+                continue
+            i_start_rp = self.first_row_above(rp, K)
+            m1_rp = (self.local_rows(rp) - i_start_rp) * nb
+            if g.pr == 1:
+                for J in tiles:
+                    ops.copy(nb, nb, Wrow, (J // g.pr - i_start_rp) * nb, m1_rp, Wcol, (J // g.pc - j_start) * nb, n1)
+                continue
+            buf = W["pack"][: len(tiles) * nb * nb]
+            ldbuf = len(tiles) * nb
+            if g.row == rp:
                 for q, J in enumerate(tiles):
-                    ops.copy(nb, nb, buf, q * nb, ldbuf, Wcol, (J // g.pc - j_start) * nb, n1)
-            # 6. trailing update, one GEMM per local tile column (rows from the diagonal tile down)
-            for j in range(j_start, self.Tc):
-                J = j * g.pc + g.col
-                i0 = self.first_row_from(g.row, J)
-                mrows = (self.Tr - i0) * nb
-                if mrows <= 0:
-                    continue
-                ops.gemm(111, 112, mrows, nb, nb, -1.0, Wrow, (i0 - i_start) * nb, m1, Wcol, (j - j_start) * nb, n1, 1.0,
-                         self.A, self.tile_off(i0, j), self.ld)
+                    ops.copy(nb, nb, Wrow, (J // g.pr - i_start_rp) * nb, m1_rp, buf, q * nb, ldbuf)
+            self._bcast(buf, rp * g.pc + g.col, g.col_group)
+            for q, J in enumerate(tiles):
+                ops.copy(nb, nb, buf, q * nb, ldbuf, Wcol, (J // g.pc - j_start) * nb, n1)
+        return {"i_start": i_start, "j_start": j_start, "m1": m1, "n1": n1, "row": Wrow, "col": Wcol}
+
+    def _update_cols(self, P, j_lo, j_hi, group: int = 4):
+        """Step 6 for local tile columns [j_lo, j_hi): A_IJ -= L_IK L_JK^T from the diagonal tile down.  Columns are
+        taken `group` at a time: one wide GEMM for the rows all of them share (below the last column's diagonal tile)
+        plus a short GEMM per column for its extra rows — fewer, larger launches keep the DMMA kernel in full waves."""
+        g, nb, ops = self.g, self.nb, self.ops
+        j_lo, j_hi = max(j_lo, P["j_start"]), min(j_hi, self.Tc)
+        ja = j_lo
+        while ja < j_hi:
+            jb = min(ja + group, j_hi)
+            i_common = self.first_row_from(g.row, (jb - 1) * g.pc + g.col)
+            mcommon = (self.Tr - i_common) * nb
+            if mcommon > 0:
+                ops.gemm(111, 112, mcommon, (jb - ja) * nb, nb, -1.0, P["row"], (i_common - P["i_start"]) * nb, P["m1"],
+                         P["col"], (ja - P["j_start"]) * nb, P["n1"], 1.0, self.A, self.tile_off(i_common, ja), self.ld)
+            for j in range(ja, jb):
+                i0 = self.first_row_from(g.row, j * g.pc + g.col)
+                i1 = min(i_common, self.Tr)
+                if i1 > i0:
+                    ops.gemm(111, 112, (i1 - i0) * nb, nb, nb, -1.0, P["row"], (i0 - P["i_start"]) * nb, P["m1"],
+                             P["col"], (j - P["j_start"]) * nb, P["n1"], 1.0, self.A, self.tile_off(i0, j), self.ld)
+            ja = jb
+
+    def potrf(self, lookahead: bool = True) -> int:
+        """Right-looking factorisation.  With `lookahead` (and an ops backend that has streams) iteration K+1's panel
+        work — diagonal factorisation, panel solve, both broadcasts — runs on a second stream as soon as tile column
+        K+1 has received iteration K's update, while the rest of iteration K's trailing update is still running."""
+        g, ops, T = self.g, self.ops, self.T
+        dist = g.dist
+        la = lookahead and hasattr(ops, "make_streams") and T > 2 and ops.make_streams()
+        if not la:
+            for K in range(T):
+                P = self._panel_phase(K)
+                if K < T - 1:
+                    self._update_cols(P, P["j_start"], self.Tc)
+        else:
+            ops.wait("panel", ops.event("update"))
+            with ops.on("panel"):
+                P = self._panel_phase(0)
+            ev_panel = ops.event("panel")
+            for K in range(T - 1):
+                ops.wait("update", ev_panel)
+                nxt = K + 1
+                j_next = nxt // g.pc if nxt % g.pc == g.col else None      # my local index of tile column K+1, if I hold it
+                with ops.on("update"):
+                    if j_next is not None:
+                        self._update_cols(P, j_next, j_next + 1)
+                ev_col = ops.event("update")
+                # enqueue the rest of iteration K's update BEFORE the host enters the next panel phase (whose diagonal
+                # factorisation returns `info` and therefore blocks the host): the update stream must never run dry
+                with ops.on("update"):
+                    if j_next is not None:
+                        self._update_cols(P, P["j_start"], j_next)
+                        self._update_cols(P, j_next + 1, self.Tc)
+                    else:
+                        self._update_cols(P, P["j_start"], self.Tc)
+                ops.wait("panel", ev_col)
+                with ops.on("panel"):
+                    Pn = self._panel_phase(nxt)
+                ev_panel = ops.event("panel")
+                P = Pn
+            ops.wait("update", ev_panel)
         # agree on info
         if dist is not None and g.world > 1:
             import torch

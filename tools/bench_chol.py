@@ -13,6 +13,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--size", dest="n", type=int, default=65536)
 ap.add_argument("--tile", dest="nb", type=int, default=512)
 ap.add_argument("--reps", type=int, default=1)
+ap.add_argument("--no-lookahead", action="store_true")
 args = ap.parse_args()
 world, rank, lr = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(lr)
@@ -32,7 +33,7 @@ for rep in range(args.reps + 1):          # first pass is the warm-up
     if dist is not None: dist.barrier()
     e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     e0.record()
-    info = ch.potrf()
+    info = ch.potrf(lookahead=not args.no_lookahead)
     e1.record()
     b = ops.empty(args.n); ops.fill_uniform(b, 0, args.n, args.n, 1, 0, 0, 777)
     x = b.clone()
