@@ -146,7 +146,8 @@ def cpu_batched_lu(ob, sample, threads):
     b = np.ascontiguousarray(synth.uniform(n, sample, SEED + 1, "d").T)
     piv = np.zeros((sample, n), np.int32)
     cpu_ref.openblas_set_threads(1)
-    ob.getrf("d", 102, n, n, A[0].copy(), n, piv[0].copy()); ob.getrs("d", 102, "N", n, 1, A[0].copy(), n, piv[0], b[0].copy(), n)
+    a0, p0, b0 = A[0].copy(), piv[0].copy(), b[0].copy()          # binds the ctypes signatures (and warms the library up)
+    ob.getrf("d", 102, n, n, a0, n, p0); ob.getrs("d", 102, "N", n, 1, a0, n, p0, b0, n)
     f_getrf = ob._cache[("getrf", "d")]; f_getrs = ob._cache[("getrs", "d")]
     drv = cpu_ref.oracle().lib.oracle_run_batched_lu_procs   # fork-parallel C loop (oracle/cpu_batch_driver.c)
     drv.restype = C.c_int
