@@ -301,15 +301,34 @@ def main():
                         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                         "config": out["batched_lu"]["config"], "roofline": out["batched_lu"]["roofline"],
                         "gpu_launches": int(total_launches)})
-    # ---------------------------------------------------------------- configs[4]: zgemm N=8192, sgemm N=16384 (1 GPU)
-    if world == 1 and args.only == "" and not args.no_other:
+    # ---------------------------------------------------------------- configs[4]: zgemm N=8192, sgemm N=16384 (same 2-D sharding)
+    if args.only == "" and not args.no_other:
         other = {}
-        del lu
+        if lu is not None:
+            del lu
         torch.cuda.empty_cache()
         for t, n, peak, bound in (("z", 8192, DMMA_PEAK_TFLOPS, "FP64 DMMA"), ("s", 16384, FFMA_PEAK_TFLOPS, "FP32 FFMA (no TF32)")):
-            ms_o, fl = jdist.time_square_gemm(t, n, reps=2)
-            tf = fl / (ms_o * 1e-3) / 1e12
-            other[f"{t}gemm_n{n}"] = {"tflops": tf, "ms": ms_o, "flop": fl, "peak_tflops": peak, "frac": tf / peak, "pipe": bound}
+            g2 = jdist.ShardedGemm(grid, n, seed=SEED, t=t)
+            for _ in range(2):
+                g2.step()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(2):
+                g2.step()
+            e1.record(stream)
+            barrier()
+            ms_o = e0.elapsed_time(e1) / 2
+            if dist is not None:
+                tms = torch.tensor([ms_o], device="cuda", dtype=torch.float64)
+                dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+                ms_o = float(tms.item())
+            g2.verify_sample(samples=3)
+            tf = g2.flop / (ms_o * 1e-3) / 1e12
+            other[f"{t}gemm_n{n}"] = {"tflops": tf, "ms": ms_o, "flop": g2.flop, "peak_tflops": peak * world, "frac": tf / (peak * world),
+                                      "pipe": bound, "n_gpus": world}
+            del g2
+            torch.cuda.empty_cache()
         out["other_configs"] = other
     # ---------------------------------------------------------------- e2e through the C ABI with host buffers
     if "gemm" in res and not args.no_e2e:

@@ -110,16 +110,24 @@ def summa_step(plan, grid: ProcessGrid, a_panels, b_panels, local_gemm):
 class ShardedGemm:
     """configs[1]: one FP64 N x N x N product, 2-D sharded; a step = panel broadcasts + local GEMMs."""
 
-    def __init__(self, grid: ProcessGrid, n: int, seed: int):
+    _TORCH = {"s": "float32", "d": "float64", "c": "complex64", "z": "complex128"}
+
+    def __init__(self, grid: ProcessGrid, n: int, seed: int, t: str = "d"):
         import torch
         from ._lib import lib, check
         self.torch, self.lib, self.check = torch, lib, check
-        self.grid, self.n, self.seed = grid, n, seed
+        self.grid, self.n, self.seed, self.t = grid, n, seed, t
+        self.esz = {"s": 4, "d": 8, "c": 8, "z": 16}[t]
         self.plan = gemm_plan(n, grid.pr, grid.pc, grid.row, grid.col, chunks=1 if grid.world == 1 else 16)
         P = self.plan
         dev = torch.device("cuda", torch.cuda.current_device())
-        f64 = torch.float64
+        f64 = getattr(torch, self._TORCH[t])
         mb, nb, w = P["mb"], P["nb"], P["w"]
+        self._gemm = getattr(lib, f"cblas_{t}gemm")
+        if t in "sd":
+            self._one, self._scal = 1.0, None
+        else:   # complex scalars travel by pointer (BlasOps.hs:156,180): [1, 0, 1] -> alpha, beta=0, beta=1
+            self._scal = np.array([1.0, 0.0, 1.0], dtype=np.complex64 if t == "c" else np.complex128)
         # column-major blocks held as flat device buffers: A row block mb x n (ld = mb; a K panel is a contiguous
         # slice), B as one w x nb buffer per K panel (ld = w)
         self.A_row = torch.empty(mb * n, dtype=f64, device=dev)
@@ -127,17 +135,28 @@ class ShardedGemm:
         self.b_panels = [torch.empty(p["w"] * nb, dtype=f64, device=dev) for p in P["panels"]]
         self.C = torch.empty(mb * nb, dtype=f64, device=dev)
         # generate only the panels this rank OWNS; the rest arrives by broadcast
+        fill = getattr(lib, f"jb_{t}fill_uniform")
+        extra = (0, 0.0) if t in "sd" else ()
         for p in P["panels"]:
             if p["a_mine"]:
-                check(lib.jb_dfill_uniform(self.a_panels[p["t"]].data_ptr(), mb, mb, p["w"], P["row0"], p["k0"], seed, 0, 0.0), "fill A")
+                check(fill(self.a_panels[p["t"]].data_ptr(), mb, mb, p["w"], P["row0"], p["k0"], seed, *extra), "fill A")
             if p["b_mine"]:
-                check(lib.jb_dfill_uniform(self.b_panels[p["t"]].data_ptr(), p["w"], p["w"], nb, p["k0"], P["col0"], seed + 1, 0, 0.0), "fill B")
+                check(fill(self.b_panels[p["t"]].data_ptr(), p["w"], p["w"], nb, p["k0"], P["col0"], seed + 1, *extra), "fill B")
         torch.cuda.synchronize()
 
+    @property
+    def flop(self) -> float:
+        return (8.0 if self.t in "cz" else 2.0) * float(self.n) ** 3
+
     def _local_gemm(self, p):
-        P, lib = self.plan, self.lib
-        lib.cblas_dgemm(102, 111, 111, P["mb"], P["nb"], p["w"], 1.0, self.a_panels[p["t"]].data_ptr(), P["mb"],
-                        self.b_panels[p["t"]].data_ptr(), p["w"], p["beta"], self.C.data_ptr(), P["mb"])
+        P = self.plan
+        if self._scal is None:
+            al, be = 1.0, p["beta"]
+        else:
+            base, isz = self._scal.ctypes.data, self._scal.itemsize
+            al, be = base, base + (2 * isz if p["beta"] else isz)
+        self._gemm(102, 111, 111, P["mb"], P["nb"], p["w"], al, self.a_panels[p["t"]].data_ptr(), P["mb"],
+                   self.b_panels[p["t"]].data_ptr(), p["w"], be, self.C.data_ptr(), P["mb"])
 
     def step(self):
         P, grid = self.plan, self.grid
@@ -169,15 +188,16 @@ class ShardedGemm:
         torch, P = self.torch, self.plan
         rng = np.random.default_rng(self.grid.rank)
         Cm = self.C.view(P["nb"], P["mb"])      # [col][row]
+        eps = np.finfo(np.float32 if self.t in "sc" else np.float64).eps
         for _ in range(samples):
             i, j = int(rng.integers(0, P["mb"])), int(rng.integers(0, P["nb"]))
-            a = synth.uniform(1, self.n, self.seed, "d", P["row0"] + i, 0)[0]
-            b = synth.uniform(self.n, 1, self.seed + 1, "d", 0, P["col0"] + j)[:, 0]
-            want = float(np.dot(a, b))
-            got = float(Cm[j, i].item())
-            tol = 4 * self.n * np.finfo(np.float64).eps * float(np.linalg.norm(a) * np.linalg.norm(b))
+            a = synth.uniform(1, self.n, self.seed, self.t, P["row0"] + i, 0)[0]
+            b = synth.uniform(self.n, 1, self.seed + 1, self.t, 0, P["col0"] + j)[:, 0]
+            want = complex(np.dot(a.astype(np.complex128), b.astype(np.complex128)))
+            got = complex(Cm[j, i].item())
+            tol = 4 * self.n * eps * float(np.linalg.norm(a) * np.linalg.norm(b))
             if not abs(got - want) <= tol:
-                raise AssertionError(f"dgemm verification failed at C[{i},{j}]: got {got}, want {want}, tol {tol}")
+                raise AssertionError(f"{self.t}gemm verification failed at C[{i},{j}]: got {got}, want {want}, tol {tol}")
 
     def e2e(self, steps=2):
         """Same metric through the reference-facing C ABI with HOST buffers: each step copies this rank's
