@@ -161,6 +161,51 @@ def cpu_batched_lu(ob, sample, threads):
             "sample": f"{sample} of the 1,000,000 systems, LAPACKE_dgetrf+dgetrs per system, C loop split over forked processes (one per core), OpenBLAS threads=1"}
 
 
+def small_config(torch, lib, check, stream):
+    """BASELINE.json configs[0]: Double 512 x 512 multiply and LU solve (gesv, nrhs = 1) — device-resident on the GPU
+    (launch-latency bound there), beside the same calls in OpenBLAS on the host."""
+    import numpy as np
+    from oracle import cpu_ref
+    n = 512
+    A = torch.empty(n * n, dtype=torch.float64, device="cuda"); B = torch.empty_like(A); Cm = torch.empty_like(A)
+    A0 = torch.empty_like(A); b0 = torch.empty(n, dtype=torch.float64, device="cuda"); b = torch.empty_like(b0)
+    check(lib.jb_dfill_uniform(A0.data_ptr(), n, n, n, 0, 0, SEED, 0, 0.0), "fill")
+    check(lib.jb_dfill_uniform(B.data_ptr(), n, n, n, 0, 0, SEED + 1, 0, 0.0), "fill")
+    check(lib.jb_dfill_uniform(b0.data_ptr(), n, n, 1, 0, 0, SEED + 2, 0, 0.0), "fill")
+    piv = (C.c_int * n)()
+
+    def ev(fn, reps):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    t_gemm = ev(lambda: lib.cblas_dgemm(102, 111, 111, n, n, n, 1.0, A0.data_ptr(), n, B.data_ptr(), n, 0.0, Cm.data_ptr(), n), 50)
+
+    def solve():
+        A.copy_(A0); b.copy_(b0)
+        assert lib.LAPACKE_dgesv(102, n, 1, A.data_ptr(), n, piv, b.data_ptr(), n) == 0
+    t_copy = ev(lambda: (A.copy_(A0), b.copy_(b0)), 20)
+    t_gesv = ev(solve, 20) - t_copy
+    ob = cpu_ref.openblas()
+    Ah = A0.cpu().numpy().reshape(n, n).T.copy(order="F"); Bh = B.cpu().numpy().reshape(n, n).T.copy(order="F")
+    Ch = np.empty((n, n), order="F"); bh = b0.cpu().numpy().copy(); ph = np.zeros(n, np.int32)
+
+    def best(f, reps):
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter(); f(); ts.append(time.perf_counter() - t0)
+        return min(ts) * 1e3
+    c_gemm = best(lambda: ob.gemm("d", 102, 111, 111, n, n, n, 1.0, Ah, n, Bh, n, 0.0, Ch, n), 20)
+    c_gesv = best(lambda: ob.gesv("d", 102, n, 1, Ah.copy(order="F"), n, ph, bh.copy(), n), 10)
+    return {"workload": "configs[0]: Double 512x512 multiply + LU solve (gesv nrhs=1), device-resident vs OpenBLAS host",
+            "gpu_dgemm_ms": t_gemm, "gpu_dgesv_ms": t_gesv, "cpu_dgemm_ms": c_gemm, "cpu_dgesv_ms": c_gesv,
+            "gpu_dgemm_tflops": 2.0 * n ** 3 / (t_gemm * 1e-3) / 1e12}
+
+
 # ------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -330,6 +375,9 @@ def main():
             del g2
             torch.cuda.empty_cache()
         out["other_configs"] = other
+    # ---------------------------------------------------------------- configs[0]: the reference's own 512 x 512 case
+    if world == 1 and args.only == "" and not args.no_other:
+        out["config0_512"] = small_config(torch, lib, check, stream)
     # ---------------------------------------------------------------- e2e through the C ABI with host buffers
     if "gemm" in res and not args.no_e2e:
         out["e2e"] = gemm.e2e(steps=min(args.steps, 2))

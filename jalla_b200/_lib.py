@@ -57,6 +57,12 @@ for _pfx in ("", "jb_"):
     _sig(_pfx + "cblas_dgemm", None, _i, _i, _i, _i, _i, _i, _d, _p, _i, _p, _i, _d, _p, _i)
     _sig(_pfx + "cblas_cgemm", None, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _i, _p, _p, _i)
     _sig(_pfx + "cblas_zgemm", None, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _i, _p, _p, _i)
+    _sig(_pfx + "cblas_ssyrk", None, _i, _i, _i, _i, _i, _f, _p, _i, _f, _p, _i)
+    _sig(_pfx + "cblas_dsyrk", None, _i, _i, _i, _i, _i, _d, _p, _i, _d, _p, _i)
+    _sig(_pfx + "cblas_csyrk", None, _i, _i, _i, _i, _i, _p, _p, _i, _p, _p, _i)
+    _sig(_pfx + "cblas_zsyrk", None, _i, _i, _i, _i, _i, _p, _p, _i, _p, _p, _i)
+    _sig(_pfx + "cblas_cherk", None, _i, _i, _i, _i, _i, _f, _p, _i, _f, _p, _i)
+    _sig(_pfx + "cblas_zherk", None, _i, _i, _i, _i, _i, _d, _p, _i, _d, _p, _i)
     _sig(_pfx + "cblas_strsm", None, _i, _i, _i, _i, _i, _i, _i, _f, _p, _i, _p, _i)
     _sig(_pfx + "cblas_dtrsm", None, _i, _i, _i, _i, _i, _i, _i, _d, _p, _i, _p, _i)
     _sig(_pfx + "cblas_ctrsm", None, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _i)

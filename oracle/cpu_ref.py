@@ -71,6 +71,18 @@ class Backend:
             sc = np.array([alpha], dtype=NP[t])
             f(order, side, uplo, trans, diag, m, n, sc.ctypes.data, _ptr(A), lda, _ptr(B), ldb)
 
+    # cblas_?syrk / cblas_?herk (OpenBLAS backends only)
+    def syrk(self, t, order, uplo, trans, n, k, alpha, A, lda, beta, Cm, ldc, herm=False):
+        name = self._gemm_name(t).replace("gemm", "herk" if herm else "syrk")
+        if herm or t in "sd":
+            sc = C.c_float if t in "sc" else C.c_double
+            f = self._fn(("syrk", t, herm), name, None, [_i] * 5 + [sc, _p, _i, sc, _p, _i])
+            f(order, uplo, trans, n, k, alpha, _ptr(A), lda, beta, _ptr(Cm), ldc)
+        else:
+            f = self._fn(("syrk", t, herm), name, None, [_i] * 5 + [_p, _p, _i, _p, _p, _i])
+            sc = np.array([alpha, beta], dtype=NP[t])
+            f(order, uplo, trans, n, k, sc.ctypes.data, _ptr(A), lda, sc.ctypes.data + sc.itemsize, _ptr(Cm), ldc)
+
     def gesv(self, t, order, n, nrhs, a, lda, ipiv, b, ldb):
         f = self._fn(("gesv", t), self._lapacke_name(t, "gesv"), _i, [_i, _i, _i, _p, _i, _p, _p, _i])
         return f(order, n, nrhs, _ptr(a), lda, _ptr(ipiv), _ptr(b), ldb)

@@ -78,6 +78,14 @@ class GpuBackend:
             keep = np.array([alpha], dtype=NP[t]); al = keep.ctypes.data
         self._run(fn, [order, side, uplo, trans, diag, m, n, al, A, lda, B, ldb], {8, 10}, {10}, "trsm", returns_info=False)
 
+    def syrk(self, t, order, uplo, trans, n, k, alpha, A, lda, beta, Cm, ldc, herm=False):
+        fn = getattr(lib, f"cblas_{t}{'herk' if herm else 'syrk'}")
+        if herm or t in "sd":
+            al, be, keep = float(alpha), float(beta), None
+        else:
+            keep = np.array([alpha, beta], dtype=NP[t]); al, be = keep.ctypes.data, keep.ctypes.data + keep.itemsize
+        self._run(fn, [order, uplo, trans, n, k, al, A, lda, be, Cm, ldc], {6, 9}, {9}, "syrk", returns_info=False)
+
     def gesv(self, t, order, n, nrhs, a, lda, ipiv, b, ldb):
         return self._run(getattr(lib, f"LAPACKE_{t}gesv"), [order, n, nrhs, a, lda, ipiv, b, ldb], {3, 6}, {3, 5, 6}, "gesv")
 

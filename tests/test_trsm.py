@@ -44,3 +44,28 @@ def test_trsm_row_major_and_large(gpu, blas, rng, t):
             gpu.trsm(t, order, side, uplo, trans, 131, m, n, 1.0, A, ka, Bg, ldb)
             blas.trsm(t, order, side, uplo, trans, 131, m, n, 1.0, A, ka, Bb, ldb)
             assert fro(Bg - Bb) / fro(Bb) <= 500 * max(m, n) * EPS[t], (side, uplo, trans, order)
+
+
+@pytest.mark.parametrize("t", "sdcz")
+@pytest.mark.parametrize("uplo", [121, 122])
+@pytest.mark.parametrize("trans", [111, 112])
+def test_syrk_herk(gpu, blas, rng, t, uplo, trans):
+    """cblas_?syrk and cblas_?herk against OpenBLAS: one triangle written, the other untouched, both orders."""
+    n, k = 150, 90
+    for herm in ([False, True] if t in "cz" else [False]):
+        tr = trans if not (herm and trans == 112) else 113
+        for order in (102, 101):
+            rows = n if (tr == 111) == (order == 102) else k
+            cols = k if (tr == 111) == (order == 102) else n
+            A = rand(rng, t, rows, cols, rows + 2)
+            C0 = rand(rng, t, n, n, n + 1)
+            alpha, beta = (0.75, -0.5) if (herm or t in "sd") else (0.75 - 0.25j, -0.5 + 0.5j)
+            Cg, Cb = C0.copy(order="F"), C0.copy(order="F")
+            gpu.syrk(t, order, uplo, tr, n, k, alpha, A, rows + 2, beta, Cg, n + 1, herm=herm)
+            blas.syrk(t, order, uplo, tr, n, k, alpha, A, rows + 2, beta, Cb, n + 1, herm=herm)
+            assert fro(Cg[:n] - Cb[:n]) / fro(Cb[:n]) <= 50 * k * EPS[t], (herm, order)
+            # the triangle that is not referenced keeps its input bits; padding row untouched
+            lower_stored = (uplo == 122) == (order == 102)
+            other = np.triu_indices(n, 1) if lower_stored else np.tril_indices(n, -1)
+            np.testing.assert_array_equal(Cg[:n][other], C0[:n][other])
+            assert np.isnan(Cg[n:]).all()
