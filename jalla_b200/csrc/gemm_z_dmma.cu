@@ -210,7 +210,11 @@ static int launch(const CUtensorMap &ma, const CUtensorMap &mb, int m, int n, in
     attr = true;
   }
   const int ntiles = ((m + BM - 1) / BM) * ((n + BN - 1) / BN);
-  const int grid = ntiles < num_sms() ? ntiles : num_sms();
+  int grid = ntiles < num_sms() ? ntiles : num_sms();
+  // "gemm.max_ctas": a CTA of this persistent kernel owns a whole SM (registers + shared memory), so callers that
+  // overlap it with other kernels — the NCCL panel broadcasts of the sharded GEMM — leave a few SMs free
+  const int cap = option("gemm.max_ctas");
+  if (cap > 0 && cap < grid) grid = cap;
   zgemm_dmma_kernel<A_KM, B_KM><<<grid, THREADS, SMEM_BYTES, s>>>(ma, mb, m, n, k, alpha, beta, C, ldc, tri, ca, cb);
   count_launch();
   JB_CUDA(cudaGetLastError());
