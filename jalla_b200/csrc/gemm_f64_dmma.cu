@@ -238,6 +238,9 @@ int dgemm_dmma_try(int ta, int tb, int m, int n, int k, double alpha, const doub
                    double beta, double *C, int ldc, cudaStream_t s, int tri) {
   using namespace dmma;
   if (m < 64 || n < 64 || k < 1) return 0;
+  // a 128x128 tile keeps one SM busy for 2*128*128*k flop: below ~64 tiles the generic kernel's smaller tiles finish
+  // sooner because they spread over all SMs (512^3: 74 us here vs ~20 us there)
+  if ((long)((m + BM - 1) / BM) * ((n + BN - 1) / BN) < 64 && option("gemm.force_dmma") <= 0) return 0;
   // TMA needs 16-byte aligned bases and row pitches
   if (((uintptr_t)A & 15) || ((uintptr_t)B & 15) || (lda & 1) || (ldb & 1)) return 0;
   const bool a_km = (ta != 111), b_km = (tb == 111);

@@ -90,7 +90,9 @@ gemm_generic_kernel(int ta, int tb, int m, int n, int k, T alpha, const T *__res
 template <typename T>
 static int launch_generic(int ta, int tb, int m, int n, int k, T alpha, const T *A, int lda, const T *B, int ldb,
                           T beta, T *C, int ldc, cudaStream_t s, int tri) {
-  if (m <= 64 || n <= 64) {   // skinny shapes (nrhs=1 solves, small panels): smaller tiles, more CTAs
+  // skinny or mid-sized shapes (nrhs=1 solves, small panels, the reference's 512^3 case): smaller tiles so that
+  // the grid still covers the 148 SMs
+  if (m <= 64 || n <= 64 || (long)((m + 63) / 64) * ((n + 63) / 64) < 120) {
     constexpr int BM = 32, BN = 32, BK = 16;
     long tiles = (long)((m + BM - 1) / BM) * ((n + BN - 1) / BN);
     gemm_generic_kernel<T, BM, BN, BK, 2, 2><<<(unsigned)tiles, 256, 0, s>>>(ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri);

@@ -227,6 +227,7 @@ int zgemm_dmma_try(int ta, int tb, int m, int n, int k, cdouble alpha, const cdo
                    int ldb, cdouble beta, cdouble *C, int ldc, cudaStream_t s, int tri) {
   using namespace zdmma;
   if (m < 32 || n < 32 || k < 1) return 0;
+  if ((long)((m + BM - 1) / BM) * ((n + BN - 1) / BN) < 48 && option("gemm.force_dmma") <= 0) return 0;   // see gemm_f64_dmma.cu
   if (((uintptr_t)A & 15) || ((uintptr_t)B & 15) || ((uintptr_t)C & 15)) return 0;
   const bool a_km = (ta != 111), b_km = (tb == 111);
   const int ca = (ta == 113), cb = (tb == 113);

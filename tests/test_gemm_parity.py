@@ -17,6 +17,16 @@ pytestmark = pytest.mark.gpu
 TYPES = "sdcz"
 
 
+@pytest.fixture
+def force_dmma():
+    """Small shapes normally go to the finer-grained generic kernel; these tests want the tuned DMMA kernels' tile
+    edges, so they pin the dispatch."""
+    from jalla_b200._lib import lib
+    lib.jb_set_option(b"gemm.force_dmma", 1)
+    yield
+    lib.jb_set_option(b"gemm.force_dmma", 0)
+
+
 def run_both(gpu, orc, t, ta, tb, m, n, k, alpha, beta, rng, pad=(0, 0, 0), order=102, poison=True):
     """Builds op-shaped operands, runs GPU and oracle, returns (Cgpu, Cref, A, B) logical views."""
     ra, ca = (m, k) if ta == 111 else (k, m)
@@ -105,6 +115,12 @@ def _diag_matrix(t, rows, cols):
     return d
 
 
+def test_config1_512_default_dispatch(gpu, orc, rng):
+    """The same 512^3 Double product on whatever kernel the dispatcher picks (the finer-grained one at this size)."""
+    Cg, Cr, A, B, *_ = run_both(gpu, orc, "d", 111, 111, 512, 512, 512, 1.0, 0.0, rng)
+    assert_close("d", 512, Cg, Cr, A, B)
+
+
 @pytest.mark.parametrize("t", TYPES)
 def test_prop_matrixMultDiag(gpu, rng, t):
     """tests/Test.hs:77-94 restated: scaling the columns of `mat` by [1,2,..] equals
@@ -130,7 +146,7 @@ def test_prop_matrixMultDiag(gpu, rng, t):
 
 @pytest.mark.parametrize("t", TYPES)
 @pytest.mark.parametrize("ta,tb", list(itertools.product((111, 112), (111, 112))))
-def test_config1_512(gpu, orc, rng, t, ta, tb):
+def test_config1_512(gpu, orc, rng, t, ta, tb, force_dmma):
     """BASELINE.json configs[0]: 512 x 512 multiply (all four transpose combinations; the
     double NN case is the one the reference config names)."""
     n = 512 if t in "sd" else 256
@@ -139,7 +155,7 @@ def test_config1_512(gpu, orc, rng, t, ta, tb):
 
 
 @pytest.mark.parametrize("ta,tb", list(itertools.product((111, 112), (111, 112))))
-def test_dgemm_ragged_large(gpu, blas, rng, ta, tb):
+def test_dgemm_ragged_large(gpu, blas, rng, ta, tb, force_dmma):
     """Tile-edge coverage of the DMMA kernel: sizes that are not multiples of the 128x128x16
     tile, even leading dimensions (TMA path) with padding; checked against OpenBLAS."""
     m, n, k = 333, 270, 1031
@@ -148,7 +164,7 @@ def test_dgemm_ragged_large(gpu, blas, rng, ta, tb):
     assert_close("d", k, Cg, Cr, A, B, extra=1.0)
 
 
-def test_dgemm_generic_matches_dmma(gpu, rng):
+def test_dgemm_generic_matches_dmma(gpu, rng, force_dmma):
     """The two device paths (tuned DMMA, generic SIMT) agree to rounding on the same input."""
     from jalla_b200._lib import lib
     m, n, k = 384, 256, 320
@@ -183,7 +199,7 @@ def test_bad_arguments_are_recorded_not_fatal(gpu, rng):
 
 
 @pytest.mark.parametrize("ta,tb", [(111, 111), (112, 111), (111, 113), (113, 112)])
-def test_zgemm_ragged_large(gpu, blas, rng, ta, tb):
+def test_zgemm_ragged_large(gpu, blas, rng, ta, tb, force_dmma):
     """Tile-edge coverage of the complex DMMA kernel (64x128x8 tiles) incl. odd leading dimensions."""
     m, n, k = 201, 333, 517
     Cg, Cr, A, B, *_ = run_both(gpu, blas, "z", ta, tb, m, n, k, 0.5 - 1.5j, 1.0 + 0.5j, rng, pad=(1, 3, 2))
