@@ -78,3 +78,33 @@ def test_matrixCopy_transpose(J, rng):
         A = J.Matrix.from_numpy(a)
         np.testing.assert_array_equal(J.matrixCopy(A, J.NoTrans).to_numpy(), a)
         np.testing.assert_array_equal(J.matrixCopy(A, J.Trans).to_numpy(), a.T)
+
+
+def test_managed_memory_is_host_dereferenceable(J, rng):
+    """Jalla's generic code peeks/pokes matrix pointers on the host.  A buffer from
+    jb_malloc(JB_MEM_MANAGED) can be filled and read through a plain host pointer while the C ABI treats it as
+    device-resident (no staging copy)."""
+    import ctypes as C
+    from jalla_b200 import _lib
+    from jalla_b200._lib import lib, check, check_last
+    n = 96
+    bufs = [lib.jb_malloc(n * n * 8, _lib.JB_MEM_MANAGED) for _ in range(3)]
+    assert all(bufs)
+    try:
+        views = [np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(n * n,)) for p in bufs]
+        a = rng.uniform(-1, 1, (n, n)); b = rng.uniform(-1, 1, (n, n))
+        views[0][:] = np.asfortranarray(a).ravel(order="F")          # host "poke"
+        views[1][:] = np.asfortranarray(b).ravel(order="F")
+        views[2][:] = np.nan
+        lib.cblas_dgemm(102, 111, 111, n, n, n, 1.0, bufs[0], n, bufs[1], n, 0.0, bufs[2], n)
+        check_last("gemm"); check(lib.jb_sync(), "sync")
+        c = views[2].reshape(n, n, order="F")                          # host "peek"
+        assert fro(c - a @ b) / fro(a @ b) <= 4 * n * EPS["d"]
+        piv = (C.c_int * n)()
+        rhs = views[1][:n].copy()
+        assert lib.LAPACKE_dgesv(102, n, 1, bufs[0], n, piv, bufs[1], n) == 0
+        x = views[1][:n]
+        assert fro(a @ x - rhs) <= 1e-9
+    finally:
+        for p in bufs:
+            lib.jb_free(p)
