@@ -7,6 +7,7 @@
 // kernel, the block row is solved against the unit-lower diagonal block, and the trailing
 // matrix is updated by this library's own GEMM (gemm_device: DMMA for double).
 #include "jb_common.cuh"
+#include <atomic>
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
@@ -219,6 +220,191 @@ lu_panel_coop_kernel(int pm, int jb, T *__restrict__ Pg, int ldg, int *__restric
   }
   for (int c = 0; c < jb; c++)
     for (int r = tid; r < nr; r += nt) Pg[(r_lo + r) + (size_t)c * ldg] = S[r + (size_t)c * lds];
+}
+
+// ------------------------------------------------------------------ LU panel, rows in registers
+// The panel kernels above keep the panel in shared memory and pay an LDS + STS per element per column for the
+// rank-1 update (measured 2.3-4.4 us per column).  Here a THREAD owns a panel row.  The not-yet-eliminated part of
+// its row lives in registers, ROTATED by one position per column step — a[j] is panel column c+j at step c — so the
+// column loop stays rolled (one small loop body in the instruction cache; a fully unrolled variant was 370 KB of
+// SASS and instruction-fetch bound) while every register index is still static: the update writes
+// a[j] = a[j+1] - l*u[c+1+j].  Multipliers, final once computed, are parked in shared memory L[c][thread] and
+// written back at the end.  The pivot search per column is three redux.sync on an order-preserving integer key per
+// warp plus one shared-memory hop across the CTA's warps.
+//
+// With more rows than one CTA holds, a cooperative grid of G CTAs exchanges, per column, a 3-word record (key, row)
+// and the candidate row's entries through global scratch written as FLAGGED WORDS: every 8-byte word carries 4 bytes
+// of payload and a 4-byte tag (launch sequence * 64 + column), stored and polled with single 8-byte relaxed
+// accesses, which are single-copy atomic.  A reader therefore needs no fence, no counter and no grid barrier: it
+// polls the G records until their tags match, reduces them, then polls the winner's row.  Two L2 round trips per
+// column.  Buffers alternate with column parity: a CTA can run at most one column ahead of the slowest reader,
+// because publishing column c+1 needs every CTA's record for column c.  The launch stays cooperative so that all
+// G CTAs are co-resident while they poll.
+struct PanelLLScratch {
+  unsigned long long *rec;    // [2][G][4]        key high word, key low word, row, unused
+  unsigned long long *cand;   // [2][G][NB * W]   candidate row of each CTA, W = sizeof(T) / 4 words per entry
+  unsigned long long *diag;   // [2][NB * W]      panel row c before the interchange
+};
+
+__device__ __forceinline__ void ll_store(unsigned long long *p, unsigned data, unsigned tag) {
+  const unsigned long long w = ((unsigned long long)tag << 32) | data;
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ unsigned ll_wait(const unsigned long long *p, unsigned tag) {
+  unsigned long long w;
+  do {
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+  } while ((unsigned)(w >> 32) != tag);
+  return (unsigned)w;
+}
+
+// warp-wide (max key, then lowest row) — rows with key 0 are only kept when flagged valid by the caller
+__device__ __forceinline__ void warp_best(unsigned long long key, int row, bool valid, unsigned long long &bk, int &br) {
+  constexpr int NONE = 0x7fffffff;
+  const unsigned hi = __reduce_max_sync(0xffffffffu, valid ? (unsigned)(key >> 32) : 0u);
+  const unsigned lo = __reduce_max_sync(0xffffffffu, (valid && (unsigned)(key >> 32) == hi) ? (unsigned)key : 0u);
+  bk = ((unsigned long long)hi << 32) | lo;
+  br = __reduce_min_sync(0xffffffffu, (valid && key == bk) ? row : NONE);
+}
+
+template <typename T, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
+lu_panel_reg_kernel(int pm, int jb, T *__restrict__ Pg, int ldg, int *__restrict__ ipiv, int *info, int row_off,
+                    PanelLLScratch sc, unsigned tag0) {
+  constexpr int W = sizeof(T) / 4;
+  constexpr int NONE = 0x7fffffff;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T *Lm = reinterpret_cast<T *>(smem_raw);              // [NB][nt] multipliers of the rows of this CTA
+  __shared__ unsigned long long s_key[MAXT / 32];
+  __shared__ int s_krow[MAXT / 32];
+  // full panel rows in absolute column order; the upper halves absorb the rotated register images (columns >= NB)
+  __shared__ __align__(16) T s_cand[2 * NB], s_diag[2 * NB], s_u[2 * NB], s_d[2 * NB];
+  __shared__ int s_p;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  const int G = gridDim.x, cta = blockIdx.x, base = cta * nt;
+  const int row = base + tid;                           // panel row owned by this thread
+  const bool live = row < pm;
+  const int ncols = min(jb, pm);
+  T a[NB];
+#pragma unroll
+  for (int j = 0; j < NB; j++) a[j] = (live && j < jb) ? Pg[row + (size_t)j * ldg] : Num<T>::zero();
+  if (tid < NB) { s_u[NB + tid] = Num<T>::zero(); s_d[NB + tid] = Num<T>::zero(); s_cand[NB + tid] = Num<T>::zero(); }
+
+  for (int c = 0; c < ncols; c++) {
+    // ---- candidate: first row of maximal |re|+|im| among rows >= c; NaNs never win (key 0)
+    unsigned long long key = 0;
+    if (live && row >= c) {
+      const double v = (double)Num<T>::abs1(a[0]);
+      if (v == v) key = (unsigned long long)__double_as_longlong(v) + 1ull;
+    }
+    unsigned long long kb;
+    int br;
+    warp_best(key, row, key != 0, kb, br);
+    if (lane == 0) { s_key[warp] = kb; s_krow[warp] = br; }
+    __syncthreads();
+    {
+      const bool has = lane < nw;
+      const unsigned long long k = has ? s_key[lane] : 0ull;
+      const int r = has ? s_krow[lane] : NONE;
+      warp_best(k, r, has && r != NONE, kb, br);
+    }
+    const bool own_c = c >= base && c < base + nt;
+    if (br == NONE && own_c) { br = c; kb = 0; }        // nothing comparable: the diagonal stands (i?amax returns 1)
+    // full candidate row and full row c, absolute column order: [multipliers | rotated registers]
+    if (row == br) {
+#pragma unroll
+      for (int j = 0; j < NB; j++) s_cand[c + j] = a[j];
+    }
+    if (row == c) {
+#pragma unroll
+      for (int j = 0; j < NB; j++) s_diag[c + j] = a[j];
+    }
+    if (warp == (1 % nw) && lane < c && br != NONE) s_cand[lane] = Lm[(size_t)lane * nt + (br - base)];
+    if (warp == (2 % nw) && lane < c && own_c) s_diag[lane] = Lm[(size_t)lane * nt + (c - base)];
+    __syncthreads();
+    int p = br;
+    const T *u = s_cand, *d = s_diag;
+    if (G > 1) {
+      if (warp == 0) {
+        const unsigned tag = tag0 + c;
+        const int par = c & 1;
+        unsigned long long *rec = sc.rec + ((size_t)par * G + cta) * 4;
+        if (lane == 0) ll_store(rec + 0, (unsigned)(kb >> 32), tag);
+        if (lane == 1) ll_store(rec + 1, (unsigned)kb, tag);
+        if (lane == 2) ll_store(rec + 2, (unsigned)br, tag);
+        if (br != NONE) {
+          unsigned long long *dst = sc.cand + ((size_t)par * G + cta) * (NB * W);
+          const unsigned *src = reinterpret_cast<const unsigned *>(s_cand);
+#pragma unroll
+          for (int w = 0; w < W; w++) ll_store(dst + lane + 32 * w, src[lane + 32 * w], tag);
+        }
+        if (own_c) {
+          unsigned long long *dst = sc.diag + (size_t)par * (NB * W);
+          const unsigned *src = reinterpret_cast<const unsigned *>(s_diag);
+#pragma unroll
+          for (int w = 0; w < W; w++) ll_store(dst + lane + 32 * w, src[lane + 32 * w], tag);
+        }
+        // every CTA reduces the G records identically
+        unsigned long long gk = 0;
+        int gr = NONE;
+        for (int g = lane; g < G; g += 32) {
+          const unsigned long long *rg = sc.rec + ((size_t)par * G + g) * 4;
+          const unsigned h = ll_wait(rg + 0, tag), l = ll_wait(rg + 1, tag);
+          const int r = (int)ll_wait(rg + 2, tag);
+          const unsigned long long k = ((unsigned long long)h << 32) | l;
+          if (r != NONE && (gr == NONE || k > gk || (k == gk && r < gr))) { gk = k; gr = r; }
+        }
+        unsigned long long gbest;
+        warp_best(gk, gr, gr != NONE, gbest, p);
+        const int win = p / nt;
+        {
+          const unsigned long long *srcw = sc.cand + ((size_t)par * G + win) * (NB * W);
+          unsigned *dstw = reinterpret_cast<unsigned *>(s_u);
+#pragma unroll
+          for (int w = 0; w < W; w++) dstw[lane + 32 * w] = ll_wait(srcw + lane + 32 * w, tag);
+        }
+        if (p != c && p >= base && p < base + nt) {
+          const unsigned long long *srcw = sc.diag + (size_t)par * (NB * W);
+          unsigned *dstw = reinterpret_cast<unsigned *>(s_d);
+#pragma unroll
+          for (int w = 0; w < W; w++) dstw[lane + 32 * w] = ll_wait(srcw + lane + 32 * w, tag);
+        }
+        if (lane == 0) s_p = p;
+      }
+      __syncthreads();
+      p = s_p;
+      u = s_u;
+      d = s_d;
+    }
+    if (cta == 0 && tid == 0) ipiv[c] = p + row_off + 1;
+    // ---- interchange: panel row c is final from here on (multipliers left of the diagonal, U right of it), so
+    // it goes straight to memory from the broadcast copy; the thread that held the pivot row takes what row c held
+    if (cta == 0 && warp == 0 && lane < jb) Pg[c + (size_t)lane * ldg] = u[lane];
+    if (p != c && p >= base && p < base + nt) {
+      if (row == p) {
+#pragma unroll
+        for (int j = 0; j < NB; j++) a[j] = d[c + j];
+      }
+      if (warp == (1 % nw) && lane < c) Lm[(size_t)lane * nt + (p - base)] = d[lane];
+    }
+    const T piv = u[c];
+    const bool zero = Num<T>::is_zero(piv);
+    if (zero && cta == 0 && tid == 0 && *info == 0) *info = c + row_off + 1;
+    const T rinv = zero ? Num<T>::zero() : Num<T>::recip(piv);
+    if (live && row > c) {
+      T l = a[0];
+      if (!zero) l = Num<T>::cmul(l, rinv);
+      Lm[(size_t)c * nt + tid] = l;
+      // eliminate and rotate: register j takes panel column c+1+j (columns >= NB are dead weight)
+#pragma unroll
+      for (int j = 0; j + 1 < NB; j++) a[j] = Num<T>::msub(a[j + 1], l, u[c + 1 + j]);
+      a[NB - 1] = Num<T>::zero();
+    }
+  }
+  __syncthreads();
+  if (live && row >= ncols) {
+    for (int j = 0; j < ncols; j++) Pg[row + (size_t)j * ldg] = Lm[(size_t)j * nt + tid];
+  }
 }
 
 // Applies interchanges ipiv[k0..k1) (1-based rows of the whole matrix; A points at its row `row_base`) to columns
@@ -475,18 +661,62 @@ __global__ void permute_rows_kernel(int inverse, int n, int nrhs, const int *__r
 }
 
 // ------------------------------------------------------------------ host-side drivers
+template <typename T> struct PanelMaxThreads { static constexpr int value = sizeof(T) == 16 ? 256 : 512; };
+struct PanelCtx {
+  int variant = 0;            // 0: rows-in-registers panel kernel, 1: the shared-memory panel kernels
+  int panel_rows = 256;       // rows (= threads) per CTA of the cooperative register panel
+  int coop_min_rows = 1024;   // shared-memory kernels: from this many rows on, the multi-CTA one
+  PanelScratch sc{};
+  bool have_sc = false;
+  PanelLLScratch ll{};
+  bool have_ll = false;
+};
+// Tags of the flagged-word exchange must never repeat on memory a previous launch may have left behind.
+static unsigned next_panel_tag() {
+  static std::atomic<unsigned> seq{1};
+  return seq.fetch_add(1) * 64u + 1u;
+}
+
 // One level of the right-looking LU with NB = 32 panels on the m x n block at A, whose first row is row
 // `row_base` of the caller's matrix (ipiv / info are written in the caller's numbering; d_ipiv is indexed locally).
 template <typename T>
-static int getrf_nb32(int m, int n, T *A, int lda, int *d_ipiv, int *d_info, int row_base, PanelScratch sc, bool have_scratch,
-                      int coop_min_rows, cudaStream_t s) {
+static int getrf_nb32(int m, int n, T *A, int lda, int *d_ipiv, int *d_info, int row_base, const PanelCtx &ctx, cudaStream_t s) {
   const int mn = m < n ? m : n;
   const size_t smem_cap = 200 * 1024;
   const int nsm = num_sms();
+  PanelScratch sc = ctx.sc;
+  const bool have_scratch = ctx.have_sc;
+  const int coop_min_rows = ctx.coop_min_rows;
+  constexpr int MAXT = PanelMaxThreads<T>::value;
   for (int j0 = 0; j0 < mn; j0 += NB) {
     const int jb = (mn - j0 < NB) ? (mn - j0) : NB;
     const int pm = m - j0;
-    if (have_scratch && pm >= coop_min_rows) {
+    // rows-in-registers panel: one CTA up to MAXT rows, a cooperative grid with flagged-word exchange above
+    int reg_nt = 0, reg_G = 0;
+    if (ctx.variant == 0) {
+      if (pm <= MAXT) { reg_nt = ((pm + 31) / 32) * 32; reg_G = 1; }
+      else if (ctx.have_ll) {
+        reg_nt = ctx.panel_rows > MAXT ? MAXT : ctx.panel_rows;
+        while ((pm + reg_nt - 1) / reg_nt > nsm && reg_nt < MAXT) reg_nt *= 2;
+        reg_G = (pm + reg_nt - 1) / reg_nt;
+        if (reg_G > nsm) reg_G = 0;
+      }
+    }
+    if (reg_G > 0) {
+      T *Pp = A + j0 + (size_t)j0 * lda;
+      int *pv = d_ipiv + j0;
+      int ldp = lda, roff = row_base + j0, jbb = jb, pmm = pm;
+      PanelLLScratch ll = ctx.ll;
+      unsigned tag0 = next_panel_tag();
+      const size_t shm = (size_t)NB * reg_nt * sizeof(T);
+      if (reg_G == 1) {
+        lu_panel_reg_kernel<T, MAXT><<<1, reg_nt, shm, s>>>(pmm, jbb, Pp, ldp, pv, d_info, roff, ll, tag0);
+      } else {
+        void *args[] = {&pmm, &jbb, &Pp, &ldp, &pv, &d_info, &roff, &ll, &tag0};
+        JB_CUDA(cudaLaunchCooperativeKernel((void *)lu_panel_reg_kernel<T, MAXT>, dim3(reg_G), dim3(reg_nt), args, shm, s));
+      }
+      count_launch();
+    } else if (have_scratch && pm >= coop_min_rows) {
       int rows_per_cta = 128;
       int G = (pm + rows_per_cta - 1) / rows_per_cta;
       if (G > nsm) { G = nsm; rows_per_cta = ((pm + G - 1) / G + 31) / 32 * 32; G = (pm + rows_per_cta - 1) / rows_per_cta; }
@@ -541,32 +771,47 @@ int getrf_device(int m, int n, T *A, int lda, int *d_ipiv, int *d_info, cudaStre
   if (mn <= 0) return 0;
   const size_t smem_cap = 200 * 1024;
   JB_CUDA(cudaFuncSetAttribute(lu_panel_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
-  const int coop_min_rows = option("getrf.coop_min_rows") > 0 ? option("getrf.coop_min_rows") : 1024;
   const int nsm = num_sms();
-  unsigned char *scratch = nullptr;
-  PanelScratch sc{};
-  if (m >= coop_min_rows) {
+  constexpr int MAXT = PanelMaxThreads<T>::value;
+  JB_CUDA(cudaFuncSetAttribute(lu_panel_reg_kernel<T, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)((size_t)NB * MAXT * sizeof(T))));
+  constexpr int W = sizeof(T) / 4;
+  PanelCtx ctx;
+  ctx.variant = option("getrf.panel_variant") > 0 ? 1 : 0;
+  if (option("getrf.panel_rows") > 0) ctx.panel_rows = (option("getrf.panel_rows") + 31) / 32 * 32;
+  if (option("getrf.coop_min_rows") > 0) ctx.coop_min_rows = option("getrf.coop_min_rows");
+  unsigned char *scratch = nullptr, *scratch_ll = nullptr;
+  if (ctx.variant == 0 && m > MAXT) {
+    const size_t words = 2 * ((size_t)nsm * 4 + (size_t)nsm * NB * W + (size_t)NB * W);
+    if (int rc = ws_alloc((void **)&scratch_ll, words * sizeof(unsigned long long), s)) return rc;
+    JB_CUDA(cudaMemsetAsync(scratch_ll, 0, words * sizeof(unsigned long long), s));
+    ctx.ll.rec = (unsigned long long *)scratch_ll;
+    ctx.ll.cand = ctx.ll.rec + 2 * (size_t)nsm * 4;
+    ctx.ll.diag = ctx.ll.cand + 2 * (size_t)nsm * NB * W;
+    ctx.have_ll = true;
+  }
+  if (m >= ctx.coop_min_rows && (ctx.variant == 1 || m > (long)nsm * MAXT)) {
     const size_t per = 2 * ((size_t)nsm * (sizeof(double) + sizeof(int) + NB * sizeof(T)) + NB * sizeof(T)) + 256;
-    if (int rc = ws_alloc((void **)&scratch, per, s)) return rc;
+    if (int rc = ws_alloc((void **)&scratch, per, s)) { ws_free(scratch_ll, s); return rc; }
     unsigned char *q = scratch;
-    sc.cand_val = (double *)q; q += 2 * (size_t)nsm * sizeof(double);
-    sc.cand_row = (int *)q; q += 2 * (size_t)nsm * sizeof(int);
+    ctx.sc.cand_val = (double *)q; q += 2 * (size_t)nsm * sizeof(double);
+    ctx.sc.cand_row = (int *)q; q += 2 * (size_t)nsm * sizeof(int);
     q = (unsigned char *)(((uintptr_t)q + 15) & ~(uintptr_t)15);
-    sc.cand_data = q; q += 2 * (size_t)nsm * NB * sizeof(T);
-    sc.diag_data = q;
+    ctx.sc.cand_data = q; q += 2 * (size_t)nsm * NB * sizeof(T);
+    ctx.sc.diag_data = q;
+    ctx.have_sc = true;
     JB_CUDA(cudaFuncSetAttribute(lu_panel_coop_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
   }
   int NB2 = option("getrf.nb2");
   if (NB2 <= 0) NB2 = (mn >= 4096) ? 256 : mn;
   int rc = 0;
   if (mn <= NB2 + NB) {
-    rc = getrf_nb32<T>(m, n, A, lda, d_ipiv, d_info, 0, sc, scratch != nullptr, coop_min_rows, s);
+    rc = getrf_nb32<T>(m, n, A, lda, d_ipiv, d_info, 0, ctx, s);
   } else {
     const T minus1 = Num<T>::neg(Num<T>::one()), one = Num<T>::one();
     for (int J0 = 0; J0 < mn && !rc; J0 += NB2) {
       const int jb2 = (mn - J0 < NB2) ? (mn - J0) : NB2;
-      rc = getrf_nb32<T>(m - J0, jb2, A + J0 + (size_t)J0 * lda, lda, d_ipiv + J0, d_info, J0, sc, scratch != nullptr,
-                         coop_min_rows, s);
+      rc = getrf_nb32<T>(m - J0, jb2, A + J0 + (size_t)J0 * lda, lda, d_ipiv + J0, d_info, J0, ctx, s);
       if (rc) break;
       if (J0 > 0) rc = laswp_launch<T>(A, lda, 0, J0, d_ipiv, J0, J0 + jb2, 0, s);
       if (rc) break;
@@ -582,6 +827,7 @@ int getrf_device(int m, int n, T *A, int lda, int *d_ipiv, int *d_info, cudaStre
     }
   }
   ws_free(scratch, s);
+  ws_free(scratch_ll, s);
   if (rc) return rc;
   JB_CUDA(cudaGetLastError());
   return 0;
