@@ -244,20 +244,14 @@ struct PanelLLScratch {
   unsigned long long *rec;    // [2][G][4]        key high word, key low word, row, unused
   unsigned long long *cand;   // [2][G][NB * W]   candidate row of each CTA, W = sizeof(T) / 4 words per entry
   unsigned long long *diag;   // [2][NB * W]      panel row c before the interchange
+  long long *prof;            // optional [8] per-phase cycle sums of CTA 0 (debug option getrf.panel_prof), or null
 };
+#define JB_PROF(i) do { if (sc.prof && cta == 0 && tid == 0) { const long long t_ = clock64(); atomicAdd((unsigned long long *)&sc.prof[i], (unsigned long long)(t_ - t_prev)); t_prev = t_; } } while (0)
 
 __device__ __forceinline__ void ll_store(unsigned long long *p, unsigned data, unsigned tag) {
   const unsigned long long w = ((unsigned long long)tag << 32) | data;
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
 }
-__device__ __forceinline__ unsigned ll_wait(const unsigned long long *p, unsigned tag) {
-  unsigned long long w;
-  do {
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
-  } while ((unsigned)(w >> 32) != tag);
-  return (unsigned)w;
-}
-
 // warp-wide (max key, then lowest row) — rows with key 0 are only kept when flagged valid by the caller
 __device__ __forceinline__ void warp_best(unsigned long long key, int row, bool valid, unsigned long long &bk, int &br) {
   constexpr int NONE = 0x7fffffff;
@@ -267,7 +261,10 @@ __device__ __forceinline__ void warp_best(unsigned long long key, int row, bool 
   br = __reduce_min_sync(0xffffffffu, (valid && key == bk) ? row : NONE);
 }
 
-template <typename T, int MAXT>
+constexpr int PANEL_REC_PER_LANE = 5;     // the record poll covers G <= 160 CTAs
+constexpr int PANEL_MULTI_THREADS = 256;  // rows per CTA of the multi-CTA instantiation (registers to spare)
+
+template <typename T, int MAXT, bool MULTI>
 __global__ void __launch_bounds__(MAXT, 1)
 lu_panel_reg_kernel(int pm, int jb, T *__restrict__ Pg, int ldg, int *__restrict__ ipiv, int *info, int row_off,
                     PanelLLScratch sc, unsigned tag0) {
@@ -290,6 +287,7 @@ lu_panel_reg_kernel(int pm, int jb, T *__restrict__ Pg, int ldg, int *__restrict
   for (int j = 0; j < NB; j++) a[j] = (live && j < jb) ? Pg[row + (size_t)j * ldg] : Num<T>::zero();
   if (tid < NB) { s_u[NB + tid] = Num<T>::zero(); s_d[NB + tid] = Num<T>::zero(); s_cand[NB + tid] = Num<T>::zero(); }
 
+  long long t_prev = clock64();
   for (int c = 0; c < ncols; c++) {
     // ---- candidate: first row of maximal |re|+|im| among rows >= c; NaNs never win (key 0)
     unsigned long long key = 0;
@@ -302,6 +300,7 @@ lu_panel_reg_kernel(int pm, int jb, T *__restrict__ Pg, int ldg, int *__restrict
     warp_best(key, row, key != 0, kb, br);
     if (lane == 0) { s_key[warp] = kb; s_krow[warp] = br; }
     __syncthreads();
+    JB_PROF(0);
     {
       const bool has = lane < nw;
       const unsigned long long k = has ? s_key[lane] : 0ull;
@@ -310,28 +309,29 @@ lu_panel_reg_kernel(int pm, int jb, T *__restrict__ Pg, int ldg, int *__restrict
     }
     const bool own_c = c >= base && c < base + nt;
     if (br == NONE && own_c) { br = c; kb = 0; }        // nothing comparable: the diagonal stands (i?amax returns 1)
+    if (MULTI && warp == 0 && lane < 3) {               // the record leaves first; the row follows while it travels
+      const unsigned v = lane == 0 ? (unsigned)(kb >> 32) : lane == 1 ? (unsigned)kb : (unsigned)br;
+      ll_store(sc.rec + ((size_t)(c & 1) * G + cta) * 4 + lane, v, tag0 + c);
+    }
     // full candidate row and full row c, absolute column order: [multipliers | rotated registers]
     if (row == br) {
 #pragma unroll
       for (int j = 0; j < NB; j++) s_cand[c + j] = a[j];
     }
-    if (row == c) {
+    if (row == c && (MULTI || br != c)) {
 #pragma unroll
       for (int j = 0; j < NB; j++) s_diag[c + j] = a[j];
     }
     if (warp == (1 % nw) && lane < c && br != NONE) s_cand[lane] = Lm[(size_t)lane * nt + (br - base)];
     if (warp == (2 % nw) && lane < c && own_c) s_diag[lane] = Lm[(size_t)lane * nt + (c - base)];
     __syncthreads();
+    JB_PROF(1);
     int p = br;
     const T *u = s_cand, *d = s_diag;
-    if (G > 1) {
+    if constexpr (MULTI) {
       if (warp == 0) {
         const unsigned tag = tag0 + c;
         const int par = c & 1;
-        unsigned long long *rec = sc.rec + ((size_t)par * G + cta) * 4;
-        if (lane == 0) ll_store(rec + 0, (unsigned)(kb >> 32), tag);
-        if (lane == 1) ll_store(rec + 1, (unsigned)kb, tag);
-        if (lane == 2) ll_store(rec + 2, (unsigned)br, tag);
         if (br != NONE) {
           unsigned long long *dst = sc.cand + ((size_t)par * G + cta) * (NB * W);
           const unsigned *src = reinterpret_cast<const unsigned *>(s_cand);
@@ -344,34 +344,80 @@ lu_panel_reg_kernel(int pm, int jb, T *__restrict__ Pg, int ldg, int *__restrict
 #pragma unroll
           for (int w = 0; w < W; w++) ll_store(dst + lane + 32 * w, src[lane + 32 * w], tag);
         }
-        // every CTA reduces the G records identically
+        JB_PROF(2);
+        // every CTA reduces the G records identically; all of a lane's records are polled together
         unsigned long long gk = 0;
         int gr = NONE;
-        for (int g = lane; g < G; g += 32) {
-          const unsigned long long *rg = sc.rec + ((size_t)par * G + g) * 4;
-          const unsigned h = ll_wait(rg + 0, tag), l = ll_wait(rg + 1, tag);
-          const int r = (int)ll_wait(rg + 2, tag);
-          const unsigned long long k = ((unsigned long long)h << 32) | l;
-          if (r != NONE && (gr == NONE || k > gk || (k == gk && r < gr))) { gk = k; gr = r; }
+        {
+          bool ok;
+          unsigned long long w0[PANEL_REC_PER_LANE], w1[PANEL_REC_PER_LANE], w2[PANEL_REC_PER_LANE];
+          do {
+#pragma unroll
+            for (int i = 0; i < PANEL_REC_PER_LANE; i++) {
+              const int g = lane + 32 * i;
+              if (g < G) {
+                const unsigned long long *rg = sc.rec + ((size_t)par * G + g) * 4;
+                asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w0[i]) : "l"(rg) : "memory");
+                asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w1[i]) : "l"(rg + 1) : "memory");
+                asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w2[i]) : "l"(rg + 2) : "memory");
+              }
+            }
+            ok = true;
+#pragma unroll
+            for (int i = 0; i < PANEL_REC_PER_LANE; i++)
+              if (lane + 32 * i < G)
+                ok = ok && (unsigned)(w0[i] >> 32) == tag && (unsigned)(w1[i] >> 32) == tag && (unsigned)(w2[i] >> 32) == tag;
+          } while (!ok);
+#pragma unroll
+          for (int i = 0; i < PANEL_REC_PER_LANE; i++)
+            if (lane + 32 * i < G) {
+              const unsigned long long k = ((unsigned long long)(unsigned)w0[i] << 32) | (unsigned)w1[i];
+              const int r = (int)(unsigned)w2[i];
+              if (r != NONE && (gr == NONE || k > gk || (k == gk && r < gr))) { gk = k; gr = r; }
+            }
         }
         unsigned long long gbest;
         warp_best(gk, gr, gr != NONE, gbest, p);
+        JB_PROF(3);
         const int win = p / nt;
+        const bool need_d = p != c && p >= base && p < base + nt;
         {
-          const unsigned long long *srcw = sc.cand + ((size_t)par * G + win) * (NB * W);
-          unsigned *dstw = reinterpret_cast<unsigned *>(s_u);
+          // the winner's row and, where this CTA holds row p, old row c: one round trip
+          unsigned uw[W], dw[W];
+          const unsigned long long *srcu = sc.cand + ((size_t)par * G + win) * (NB * W);
+          const unsigned long long *srcd = sc.diag + (size_t)par * (NB * W);
+          bool ok;
+          do {
+            unsigned long long xu[W], xd[W];
 #pragma unroll
-          for (int w = 0; w < W; w++) dstw[lane + 32 * w] = ll_wait(srcw + lane + 32 * w, tag);
-        }
-        if (p != c && p >= base && p < base + nt) {
-          const unsigned long long *srcw = sc.diag + (size_t)par * (NB * W);
-          unsigned *dstw = reinterpret_cast<unsigned *>(s_d);
+            for (int w = 0; w < W; w++)
+              asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(xu[w]) : "l"(srcu + lane + 32 * w) : "memory");
+            if (need_d) {
 #pragma unroll
-          for (int w = 0; w < W; w++) dstw[lane + 32 * w] = ll_wait(srcw + lane + 32 * w, tag);
+              for (int w = 0; w < W; w++)
+                asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(xd[w]) : "l"(srcd + lane + 32 * w) : "memory");
+            }
+            ok = true;
+#pragma unroll
+            for (int w = 0; w < W; w++) { ok = ok && (unsigned)(xu[w] >> 32) == tag; uw[w] = (unsigned)xu[w]; }
+            if (need_d) {
+#pragma unroll
+              for (int w = 0; w < W; w++) { ok = ok && (unsigned)(xd[w] >> 32) == tag; dw[w] = (unsigned)xd[w]; }
+            }
+          } while (!ok);
+          unsigned *du = reinterpret_cast<unsigned *>(s_u), *dd = reinterpret_cast<unsigned *>(s_d);
+#pragma unroll
+          for (int w = 0; w < W; w++) du[lane + 32 * w] = uw[w];
+          if (need_d) {
+#pragma unroll
+            for (int w = 0; w < W; w++) dd[lane + 32 * w] = dw[w];
+          }
         }
         if (lane == 0) s_p = p;
+        JB_PROF(4);
       }
       __syncthreads();
+      JB_PROF(5);
       p = s_p;
       u = s_u;
       d = s_d;
@@ -400,6 +446,7 @@ lu_panel_reg_kernel(int pm, int jb, T *__restrict__ Pg, int ldg, int *__restrict
       for (int j = 0; j + 1 < NB; j++) a[j] = Num<T>::msub(a[j + 1], l, u[c + 1 + j]);
       a[NB - 1] = Num<T>::zero();
     }
+    JB_PROF(6);
   }
   __syncthreads();
   if (live && row >= ncols) {
@@ -696,10 +743,10 @@ static int getrf_nb32(int m, int n, T *A, int lda, int *d_ipiv, int *d_info, int
     if (ctx.variant == 0) {
       if (pm <= MAXT) { reg_nt = ((pm + 31) / 32) * 32; reg_G = 1; }
       else if (ctx.have_ll) {
-        reg_nt = ctx.panel_rows > MAXT ? MAXT : ctx.panel_rows;
-        while ((pm + reg_nt - 1) / reg_nt > nsm && reg_nt < MAXT) reg_nt *= 2;
+        reg_nt = ctx.panel_rows > PANEL_MULTI_THREADS ? PANEL_MULTI_THREADS : ctx.panel_rows;
+        while ((pm + reg_nt - 1) / reg_nt > nsm && reg_nt < PANEL_MULTI_THREADS) reg_nt *= 2;
         reg_G = (pm + reg_nt - 1) / reg_nt;
-        if (reg_G > nsm) reg_G = 0;
+        if (reg_G > nsm || reg_G < 2) reg_G = 0;      // taller than 148 x 256 rows: the shared-memory kernels
       }
     }
     if (reg_G > 0) {
@@ -710,10 +757,11 @@ static int getrf_nb32(int m, int n, T *A, int lda, int *d_ipiv, int *d_info, int
       unsigned tag0 = next_panel_tag();
       const size_t shm = (size_t)NB * reg_nt * sizeof(T);
       if (reg_G == 1) {
-        lu_panel_reg_kernel<T, MAXT><<<1, reg_nt, shm, s>>>(pmm, jbb, Pp, ldp, pv, d_info, roff, ll, tag0);
+        lu_panel_reg_kernel<T, MAXT, false><<<1, reg_nt, shm, s>>>(pmm, jbb, Pp, ldp, pv, d_info, roff, ll, tag0);
       } else {
         void *args[] = {&pmm, &jbb, &Pp, &ldp, &pv, &d_info, &roff, &ll, &tag0};
-        JB_CUDA(cudaLaunchCooperativeKernel((void *)lu_panel_reg_kernel<T, MAXT>, dim3(reg_G), dim3(reg_nt), args, shm, s));
+        JB_CUDA(cudaLaunchCooperativeKernel((void *)lu_panel_reg_kernel<T, PANEL_MULTI_THREADS, true>, dim3(reg_G),
+                                            dim3(reg_nt), args, shm, s));
       }
       count_launch();
     } else if (have_scratch && pm >= coop_min_rows) {
@@ -773,8 +821,10 @@ int getrf_device(int m, int n, T *A, int lda, int *d_ipiv, int *d_info, cudaStre
   JB_CUDA(cudaFuncSetAttribute(lu_panel_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
   const int nsm = num_sms();
   constexpr int MAXT = PanelMaxThreads<T>::value;
-  JB_CUDA(cudaFuncSetAttribute(lu_panel_reg_kernel<T, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  JB_CUDA(cudaFuncSetAttribute(lu_panel_reg_kernel<T, MAXT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)((size_t)NB * MAXT * sizeof(T))));
+  JB_CUDA(cudaFuncSetAttribute(lu_panel_reg_kernel<T, PANEL_MULTI_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)((size_t)NB * PANEL_MULTI_THREADS * sizeof(T))));
   constexpr int W = sizeof(T) / 4;
   PanelCtx ctx;
   ctx.variant = option("getrf.panel_variant") > 0 ? 1 : 0;
@@ -782,15 +832,22 @@ int getrf_device(int m, int n, T *A, int lda, int *d_ipiv, int *d_info, cudaStre
   if (option("getrf.coop_min_rows") > 0) ctx.coop_min_rows = option("getrf.coop_min_rows");
   unsigned char *scratch = nullptr, *scratch_ll = nullptr;
   if (ctx.variant == 0 && m > MAXT) {
-    const size_t words = 2 * ((size_t)nsm * 4 + (size_t)nsm * NB * W + (size_t)NB * W);
+    constexpr int PW = NB * W;            // words per row packet
+    const size_t words = 2 * ((size_t)nsm * 4 + (size_t)nsm * PW + (size_t)PW);
     if (int rc = ws_alloc((void **)&scratch_ll, words * sizeof(unsigned long long), s)) return rc;
     JB_CUDA(cudaMemsetAsync(scratch_ll, 0, words * sizeof(unsigned long long), s));
     ctx.ll.rec = (unsigned long long *)scratch_ll;
     ctx.ll.cand = ctx.ll.rec + 2 * (size_t)nsm * 4;
-    ctx.ll.diag = ctx.ll.cand + 2 * (size_t)nsm * NB * W;
+    ctx.ll.diag = ctx.ll.cand + 2 * (size_t)nsm * PW;
     ctx.have_ll = true;
   }
-  if (m >= ctx.coop_min_rows && (ctx.variant == 1 || m > (long)nsm * MAXT)) {
+  long long *prof = nullptr;
+  if (option("getrf.panel_prof") > 0) {
+    if (int rc = ws_alloc((void **)&prof, 8 * sizeof(long long), s)) return rc;
+    JB_CUDA(cudaMemsetAsync(prof, 0, 8 * sizeof(long long), s));
+    ctx.ll.prof = prof;
+  }
+  if (m >= ctx.coop_min_rows && (ctx.variant == 1 || m > (long)nsm * PANEL_MULTI_THREADS)) {
     const size_t per = 2 * ((size_t)nsm * (sizeof(double) + sizeof(int) + NB * sizeof(T)) + NB * sizeof(T)) + 256;
     if (int rc = ws_alloc((void **)&scratch, per, s)) { ws_free(scratch_ll, s); return rc; }
     unsigned char *q = scratch;
@@ -825,6 +882,14 @@ int getrf_device(int m, int n, T *A, int lda, int *d_ipiv, int *d_info, cudaStre
                               A + J0 + (size_t)(J0 + jb2) * lda, lda, one, A + (J0 + jb2) + (size_t)(J0 + jb2) * lda, lda, s, 0);
       }
     }
+  }
+  if (prof) {
+    long long h[8];
+    cudaMemcpyAsync(h, prof, sizeof(h), cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    fprintf(stderr, "[getrf.panel_prof] n=%d cycles of CTA 0 summed over %d columns: search+B1 %lld | pick+copy+B1b %lld | publish %lld | "
+            "poll records %lld | winner row %lld | B2 %lld | interchange+update %lld\n", mn, mn, h[0], h[1], h[2], h[3], h[4], h[5], h[6]);
+    ws_free(prof, s);
   }
   ws_free(scratch, s);
   ws_free(scratch_ll, s);
