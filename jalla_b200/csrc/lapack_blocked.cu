@@ -246,7 +246,10 @@ struct PanelLLScratch {
   unsigned long long *diag;   // [2][NB * W]      panel row c before the interchange
   long long *prof;            // optional [8] per-phase cycle sums of CTA 0 (debug option getrf.panel_prof), or null
 };
-#define JB_PROF(i) do { if (sc.prof && cta == 0 && tid == 0) { const long long t_ = clock64(); atomicAdd((unsigned long long *)&sc.prof[i], (unsigned long long)(t_ - t_prev)); t_prev = t_; } } while (0)
+#ifndef JB_PANEL_PROF
+#define JB_PANEL_PROF 0
+#endif
+#define JB_PROF(i) do { if (!JB_PANEL_PROF) break; if (sc.prof && cta == 0 && tid == 0) { const long long t_ = clock64(); atomicAdd((unsigned long long *)&sc.prof[i], (unsigned long long)(t_ - t_prev)); t_prev = t_; } } while (0)
 
 __device__ __forceinline__ void ll_store(unsigned long long *p, unsigned data, unsigned tag) {
   const unsigned long long w = ((unsigned long long)tag << 32) | data;
@@ -264,18 +267,24 @@ __device__ __forceinline__ void warp_best(unsigned long long key, int row, bool 
 constexpr int PANEL_REC_PER_LANE = 5;     // the record poll covers G <= 160 CTAs
 constexpr int PANEL_MULTI_THREADS = 256;  // rows per CTA of the multi-CTA instantiation (registers to spare)
 
+// A panel row as it is passed around: `rot` is the owner's register image (rot[j] = panel column c+j at step c, so
+// every access is a static, 16-byte aligned pair), `lpart` its multipliers in absolute columns 0..c-1.
+template <typename T> struct alignas(16) PanelRow { T rot[NB]; T lpart[NB]; };
+template <typename T> struct alignas(2 * sizeof(T)) PanelPair { T x, y; };
+
 template <typename T, int MAXT, bool MULTI>
 __global__ void __launch_bounds__(MAXT, 1)
 lu_panel_reg_kernel(int pm, int jb, T *__restrict__ Pg, int ldg, int *__restrict__ ipiv, int *info, int row_off,
                     PanelLLScratch sc, unsigned tag0) {
   constexpr int W = sizeof(T) / 4;
+  constexpr int PW = 2 * NB * W;                        // words per row packet
   constexpr int NONE = 0x7fffffff;
+  using Pair = PanelPair<T>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T *Lm = reinterpret_cast<T *>(smem_raw);              // [NB][nt] multipliers of the rows of this CTA
   __shared__ unsigned long long s_key[MAXT / 32];
   __shared__ int s_krow[MAXT / 32];
-  // full panel rows in absolute column order; the upper halves absorb the rotated register images (columns >= NB)
-  __shared__ __align__(16) T s_cand[2 * NB], s_diag[2 * NB], s_u[2 * NB], s_d[2 * NB];
+  __shared__ PanelRow<T> s_cand, s_diag, s_u, s_d;
   __shared__ int s_p;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
   const int G = gridDim.x, cta = blockIdx.x, base = cta * nt;
@@ -285,7 +294,6 @@ lu_panel_reg_kernel(int pm, int jb, T *__restrict__ Pg, int ldg, int *__restrict
   T a[NB];
 #pragma unroll
   for (int j = 0; j < NB; j++) a[j] = (live && j < jb) ? Pg[row + (size_t)j * ldg] : Num<T>::zero();
-  if (tid < NB) { s_u[NB + tid] = Num<T>::zero(); s_d[NB + tid] = Num<T>::zero(); s_cand[NB + tid] = Num<T>::zero(); }
 
   long long t_prev = clock64();
   for (int c = 0; c < ncols; c++) {
@@ -309,43 +317,42 @@ lu_panel_reg_kernel(int pm, int jb, T *__restrict__ Pg, int ldg, int *__restrict
     }
     const bool own_c = c >= base && c < base + nt;
     if (br == NONE && own_c) { br = c; kb = 0; }        // nothing comparable: the diagonal stands (i?amax returns 1)
+    const unsigned tag = tag0 + c;
+    const int par = c & 1;
     if (MULTI && warp == 0 && lane < 3) {               // the record leaves first; the row follows while it travels
       const unsigned v = lane == 0 ? (unsigned)(kb >> 32) : lane == 1 ? (unsigned)kb : (unsigned)br;
-      ll_store(sc.rec + ((size_t)(c & 1) * G + cta) * 4 + lane, v, tag0 + c);
+      ll_store(sc.rec + ((size_t)par * G + cta) * 4 + lane, v, tag);
     }
-    // full candidate row and full row c, absolute column order: [multipliers | rotated registers]
     if (row == br) {
 #pragma unroll
-      for (int j = 0; j < NB; j++) s_cand[c + j] = a[j];
+      for (int j = 0; j < NB; j += 2) *reinterpret_cast<Pair *>(&s_cand.rot[j]) = Pair{a[j], a[j + 1]};
     }
     if (row == c && (MULTI || br != c)) {
 #pragma unroll
-      for (int j = 0; j < NB; j++) s_diag[c + j] = a[j];
+      for (int j = 0; j < NB; j += 2) *reinterpret_cast<Pair *>(&s_diag.rot[j]) = Pair{a[j], a[j + 1]};
     }
-    if (warp == (1 % nw) && lane < c && br != NONE) s_cand[lane] = Lm[(size_t)lane * nt + (br - base)];
-    if (warp == (2 % nw) && lane < c && own_c) s_diag[lane] = Lm[(size_t)lane * nt + (c - base)];
+    if (warp == (1 % nw) && lane < c && br != NONE) s_cand.lpart[lane] = Lm[(size_t)lane * nt + (br - base)];
+    if (warp == (2 % nw) && lane < c && own_c) s_diag.lpart[lane] = Lm[(size_t)lane * nt + (c - base)];
     __syncthreads();
     JB_PROF(1);
     int p = br;
-    const T *u = s_cand, *d = s_diag;
+    const PanelRow<T> *u = &s_cand, *d = &s_diag;
     if constexpr (MULTI) {
       if (warp == 0) {
-        const unsigned tag = tag0 + c;
-        const int par = c & 1;
         if (br != NONE) {
-          unsigned long long *dst = sc.cand + ((size_t)par * G + cta) * (NB * W);
-          const unsigned *src = reinterpret_cast<const unsigned *>(s_cand);
+          unsigned long long *dst = sc.cand + ((size_t)par * G + cta) * PW;
+          const unsigned *src = reinterpret_cast<const unsigned *>(&s_cand);
 #pragma unroll
-          for (int w = 0; w < W; w++) ll_store(dst + lane + 32 * w, src[lane + 32 * w], tag);
+          for (int w = 0; w < 2 * W; w++) ll_store(dst + lane + 32 * w, src[lane + 32 * w], tag);
         }
         if (own_c) {
-          unsigned long long *dst = sc.diag + (size_t)par * (NB * W);
-          const unsigned *src = reinterpret_cast<const unsigned *>(s_diag);
+          unsigned long long *dst = sc.diag + (size_t)par * PW;
+          const unsigned *src = reinterpret_cast<const unsigned *>(&s_diag);
 #pragma unroll
-          for (int w = 0; w < W; w++) ll_store(dst + lane + 32 * w, src[lane + 32 * w], tag);
+          for (int w = 0; w < 2 * W; w++) ll_store(dst + lane + 32 * w, src[lane + 32 * w], tag);
         }
         JB_PROF(2);
-        // every CTA reduces the G records identically; all of a lane's records are polled together
+        // every CTA reduces the G records identically; a lane's records are polled together
         unsigned long long gk = 0;
         int gr = NONE;
         {
@@ -383,34 +390,34 @@ lu_panel_reg_kernel(int pm, int jb, T *__restrict__ Pg, int ldg, int *__restrict
         const bool need_d = p != c && p >= base && p < base + nt;
         {
           // the winner's row and, where this CTA holds row p, old row c: one round trip
-          unsigned uw[W], dw[W];
-          const unsigned long long *srcu = sc.cand + ((size_t)par * G + win) * (NB * W);
-          const unsigned long long *srcd = sc.diag + (size_t)par * (NB * W);
+          unsigned uw[2 * W], dw[2 * W];
+          const unsigned long long *srcu = sc.cand + ((size_t)par * G + win) * PW;
+          const unsigned long long *srcd = sc.diag + (size_t)par * PW;
           bool ok;
           do {
-            unsigned long long xu[W], xd[W];
+            unsigned long long xu[2 * W], xd[2 * W];
 #pragma unroll
-            for (int w = 0; w < W; w++)
+            for (int w = 0; w < 2 * W; w++)
               asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(xu[w]) : "l"(srcu + lane + 32 * w) : "memory");
             if (need_d) {
 #pragma unroll
-              for (int w = 0; w < W; w++)
+              for (int w = 0; w < 2 * W; w++)
                 asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(xd[w]) : "l"(srcd + lane + 32 * w) : "memory");
             }
             ok = true;
 #pragma unroll
-            for (int w = 0; w < W; w++) { ok = ok && (unsigned)(xu[w] >> 32) == tag; uw[w] = (unsigned)xu[w]; }
+            for (int w = 0; w < 2 * W; w++) { ok = ok && (unsigned)(xu[w] >> 32) == tag; uw[w] = (unsigned)xu[w]; }
             if (need_d) {
 #pragma unroll
-              for (int w = 0; w < W; w++) { ok = ok && (unsigned)(xd[w] >> 32) == tag; dw[w] = (unsigned)xd[w]; }
+              for (int w = 0; w < 2 * W; w++) { ok = ok && (unsigned)(xd[w] >> 32) == tag; dw[w] = (unsigned)xd[w]; }
             }
           } while (!ok);
-          unsigned *du = reinterpret_cast<unsigned *>(s_u), *dd = reinterpret_cast<unsigned *>(s_d);
+          unsigned *du = reinterpret_cast<unsigned *>(&s_u), *dd = reinterpret_cast<unsigned *>(&s_d);
 #pragma unroll
-          for (int w = 0; w < W; w++) du[lane + 32 * w] = uw[w];
+          for (int w = 0; w < 2 * W; w++) du[lane + 32 * w] = uw[w];
           if (need_d) {
 #pragma unroll
-            for (int w = 0; w < W; w++) dd[lane + 32 * w] = dw[w];
+            for (int w = 0; w < 2 * W; w++) dd[lane + 32 * w] = dw[w];
           }
         }
         if (lane == 0) s_p = p;
@@ -419,33 +426,42 @@ lu_panel_reg_kernel(int pm, int jb, T *__restrict__ Pg, int ldg, int *__restrict
       __syncthreads();
       JB_PROF(5);
       p = s_p;
-      u = s_u;
-      d = s_d;
+      u = &s_u;
+      d = &s_d;
     }
     if (cta == 0 && tid == 0) ipiv[c] = p + row_off + 1;
     // ---- interchange: panel row c is final from here on (multipliers left of the diagonal, U right of it), so
     // it goes straight to memory from the broadcast copy; the thread that held the pivot row takes what row c held
-    if (cta == 0 && warp == 0 && lane < jb) Pg[c + (size_t)lane * ldg] = u[lane];
+    if (cta == 0 && warp == 0 && lane < jb) Pg[c + (size_t)lane * ldg] = lane < c ? u->lpart[lane] : u->rot[lane - c];
     if (p != c && p >= base && p < base + nt) {
       if (row == p) {
 #pragma unroll
-        for (int j = 0; j < NB; j++) a[j] = d[c + j];
+        for (int j = 0; j < NB; j += 2) {
+          const Pair q = *reinterpret_cast<const Pair *>(&d->rot[j]);
+          a[j] = q.x; a[j + 1] = q.y;
+        }
       }
-      if (warp == (1 % nw) && lane < c) Lm[(size_t)lane * nt + (p - base)] = d[lane];
+      if (warp == (1 % nw) && lane < c) Lm[(size_t)lane * nt + (p - base)] = d->lpart[lane];
     }
-    const T piv = u[c];
+    const Pair *up = reinterpret_cast<const Pair *>(u->rot);
+    const Pair u0 = up[0];
+    const T piv = u0.x;
     const bool zero = Num<T>::is_zero(piv);
     if (zero && cta == 0 && tid == 0 && *info == 0) *info = c + row_off + 1;
     const T rinv = zero ? Num<T>::zero() : Num<T>::recip(piv);
-    if (live && row > c) {
-      T l = a[0];
-      if (!zero) l = Num<T>::cmul(l, rinv);
-      Lm[(size_t)c * nt + tid] = l;
-      // eliminate and rotate: register j takes panel column c+1+j (columns >= NB are dead weight)
+    // ---- eliminate and rotate: register j takes panel column c+1+j.  Rows <= c are dead from here on and
+    // compute garbage that nothing reads (their keys are 0, their Lm slots are never consulted).
+    T l = a[0];
+    if (!zero) l = Num<T>::cmul(l, rinv);
+    Lm[(size_t)c * nt + tid] = l;
+    a[0] = Num<T>::msub(a[1], l, u0.y);
 #pragma unroll
-      for (int j = 0; j + 1 < NB; j++) a[j] = Num<T>::msub(a[j + 1], l, u[c + 1 + j]);
-      a[NB - 1] = Num<T>::zero();
+    for (int jj = 1; jj < NB / 2; jj++) {
+      const Pair q = up[jj];
+      a[2 * jj - 1] = Num<T>::msub(a[2 * jj], l, q.x);
+      a[2 * jj] = Num<T>::msub(a[2 * jj + 1], l, q.y);
     }
+    a[NB - 1] = Num<T>::zero();
     JB_PROF(6);
   }
   __syncthreads();
@@ -832,7 +848,7 @@ int getrf_device(int m, int n, T *A, int lda, int *d_ipiv, int *d_info, cudaStre
   if (option("getrf.coop_min_rows") > 0) ctx.coop_min_rows = option("getrf.coop_min_rows");
   unsigned char *scratch = nullptr, *scratch_ll = nullptr;
   if (ctx.variant == 0 && m > MAXT) {
-    constexpr int PW = NB * W;            // words per row packet
+    constexpr int PW = 2 * NB * W;        // words per row packet
     const size_t words = 2 * ((size_t)nsm * 4 + (size_t)nsm * PW + (size_t)PW);
     if (int rc = ws_alloc((void **)&scratch_ll, words * sizeof(unsigned long long), s)) return rc;
     JB_CUDA(cudaMemsetAsync(scratch_ll, 0, words * sizeof(unsigned long long), s));
