@@ -682,6 +682,92 @@ potf2_block_kernel(int lower, int jb, T *__restrict__ A, int lda, int *info, int
   if (threadIdx.x == 0 && s_fail) *info = off + s_fail;
 }
 
+// ------------------------------------------------------------------ Cholesky panel, rows in registers
+// Factorises a panel of the lower-form matrix — its jb x jb diagonal block AND every row below it — in one launch:
+// potf2 on the block and the triangular solve of the rows under it, fused.  Same register scheme as the LU panel
+// (a thread owns a row, the part not yet eliminated is rotated through its registers, finished multipliers wait in
+// shared memory), but without a pivot search the only thing a column step needs from another thread is row c of
+// the diagonal block, scaled: u[j] = conj(L[c+j][c]).  Warp 0 of EVERY CTA carries the <= 32 diagonal-block rows
+// redundantly (mirrored to full Hermitian rows on load, only the stored triangle is read), so CTAs never talk to
+// each other and the grid needs no co-residency: CTA g owns rows 32 + g*(NT-32) ... and CTA 0 alone writes the
+// diagonal block back.  Row c's owner posts its scaled row before the column's single barrier (double buffered by
+// column parity).  Arithmetic per entry is potf2's: s = sqrt(d), l = a * (1/s), a -= l * conj(l').
+// `lower == 0` runs the same code on the conjugate-transposed addressing (the panel is then a block row of U).
+// info = first non-positive (or NaN) pivot, 1-based + off; the panel is then left partially factored like ?potf2.
+constexpr int CHOL_PANEL_THREADS = 256;
+template <typename T>
+__global__ void __launch_bounds__(CHOL_PANEL_THREADS, 1)
+chol_panel_kernel(int lower, int m, int jb, T *__restrict__ P, int lda, int *info, int off) {
+  if (*info) return;
+  using R = typename Num<T>::R;
+  using Pair = PanelPair<T>;
+  constexpr int NT = CHOL_PANEL_THREADS;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T *Lm = reinterpret_cast<T *>(smem_raw);              // [NB][NT] finished multipliers of this CTA's rows
+  struct alignas(16) Posted { T rot[NB]; R rinv; int fail; };
+  __shared__ Posted s_u[2];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int row = warp == 0 ? tid : NB + blockIdx.x * (NT - NB) + (tid - NB);
+  const bool live = row < m;
+  const bool writer = live && (warp != 0 || blockIdx.x == 0);
+  auto at = [&](int r, int j) -> T * { return lower ? P + r + (size_t)j * lda : P + j + (size_t)r * lda; };
+  T a[NB];
+#pragma unroll
+  for (int j = 0; j < NB; j++) {
+    T v = Num<T>::zero();
+    if (live && j < jb) {
+      // rows of the diagonal block are completed from the stored triangle: (r, j>r) = conj((j, r))
+      const bool mirror = row < jb && j > row;
+      v = mirror ? *at(j, row) : *at(row, j);
+      if (mirror != (lower == 0)) v = Num<T>::conj(v);
+    }
+    a[j] = v;
+  }
+  int failed_at = -1;
+  for (int c = 0; c < jb; c++) {
+    const int par = c & 1;
+    if (row == c) {
+      const R d = Num<T>::re(a[0]);
+      const bool ok = d > (R)0;
+      const R sq = sqrt(d), rinv = (R)1 / sq;
+      s_u[par].fail = !ok;
+      s_u[par].rinv = rinv;
+      s_u[par].rot[0] = Num<T>::make(sq, 0);
+#pragma unroll
+      for (int j = 1; j < NB; j++) s_u[par].rot[j] = Num<T>::scale(a[j], rinv);
+    }
+    __syncthreads();
+    if (s_u[par].fail) { failed_at = c; break; }
+    const Pair *up = reinterpret_cast<const Pair *>(s_u[par].rot);
+    const Pair u0 = up[0];
+    // rows above c are finished and compute garbage nothing reads; row c parks the diagonal entry
+    const T l = row == c ? u0.x : Num<T>::scale(a[0], s_u[par].rinv);
+    Lm[(size_t)c * NT + tid] = l;
+    a[0] = Num<T>::msub(a[1], l, u0.y);
+#pragma unroll
+    for (int jj = 1; jj < NB / 2; jj++) {
+      const Pair q = up[jj];
+      a[2 * jj - 1] = Num<T>::msub(a[2 * jj], l, q.x);
+      a[2 * jj] = Num<T>::msub(a[2 * jj + 1], l, q.y);
+    }
+    a[NB - 1] = Num<T>::zero();
+  }
+  if (failed_at >= 0 && blockIdx.x == 0 && tid == 0) *info = off + failed_at + 1;
+  if (!writer) return;
+  if (failed_at >= 0) {
+    // columns [0, failed_at) are final; park the partially updated rest (a[k] = column failed_at + k) next to them
+#pragma unroll
+    for (int k = 0; k < NB; k++)
+      if (failed_at + k < NB) Lm[(size_t)(failed_at + k) * NT + tid] = a[k];
+  }
+  const int last = row < jb ? row : jb - 1;             // only the stored triangle of the diagonal block
+  for (int j = 0; j <= last; j++) {
+    T v = Lm[(size_t)j * NT + tid];
+    if (!lower) v = Num<T>::conj(v);
+    *at(row, j) = v;
+  }
+}
+
 // ------------------------------------------------------------------ helpers for getri / getrs
 template <typename T>
 __global__ void set_identity_kernel(int n, T *W, int ldw) {
@@ -876,7 +962,8 @@ int getrf_device(int m, int n, T *A, int lda, int *d_ipiv, int *d_info, cudaStre
     JB_CUDA(cudaFuncSetAttribute(lu_panel_coop_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
   }
   int NB2 = option("getrf.nb2");
-  if (NB2 <= 0) NB2 = (mn >= 4096) ? 256 : mn;
+  // measured (tools/time_nb2.py): 16384: 212.8 / 185.7 / 178.2 / 175.4 ms for 128 / 256 / 384 / 512; 8192: 46.6 / 43.9 / 43.6 / 43.2
+  if (NB2 <= 0) NB2 = (mn >= 8192) ? 512 : (mn >= 4096 ? 256 : mn);
   int rc = 0;
   if (mn <= NB2 + NB) {
     rc = getrf_nb32<T>(m, n, A, lda, d_ipiv, d_info, 0, ctx, s);
@@ -1040,6 +1127,43 @@ static int potrf_nb32(int lower, int nn, T *A, int lda, int *d_info, int off, cu
   return 0;
 }
 
+// Two-level right-looking Cholesky.  Inside an outer block of NB2 columns every 32-column panel is factorised over
+// ALL rows below it by chol_panel_kernel (diagonal block + solve in one launch) and only the remaining columns of
+// the outer block are updated (a skinny rank-32 GEMM); the trailing matrix then gets ONE rank-NB2 update per outer
+// step through the tuned GEMM in triangle mode (DMMA for double / complex double).
+template <typename T>
+static int potrf_panels(char uplo, int n, T *A, int lda, int *d_info, int NB2, cudaStream_t s) {
+  const int lower = (uplo == 'L' || uplo == 'l');
+  const T minus1 = Num<T>::neg(Num<T>::one()), one = Num<T>::one();
+  const int tc = Num<T>::cplx ? 113 : 112;
+  const size_t shm = (size_t)NB * CHOL_PANEL_THREADS * sizeof(T);
+  JB_CUDA(cudaFuncSetAttribute(chol_panel_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+  // C[r0:, c0:c1] -= L[r0:, k0:k1] * L[c0:c1, k0:k1]^H in lower form (rows >= columns only), or its mirror image
+  auto update = [&](int r0, int c0, int c1, int k0, int k1) -> int {
+    const int mr = n - r0, nc = c1 - c0, kk = k1 - k0;
+    if (mr <= 0 || nc <= 0) return 0;
+    if (lower)
+      return gemm_device<T>(111, tc, mr, nc, kk, minus1, A + r0 + (size_t)k0 * lda, lda, A + c0 + (size_t)k0 * lda, lda, one,
+                            A + r0 + (size_t)c0 * lda, lda, s, 'L');
+    return gemm_device<T>(tc, 111, nc, mr, kk, minus1, A + k0 + (size_t)c0 * lda, lda, A + k0 + (size_t)r0 * lda, lda, one,
+                          A + c0 + (size_t)r0 * lda, lda, s, 'U');
+  };
+  for (int J0 = 0; J0 < n; J0 += NB2) {
+    const int jb2 = (n - J0 < NB2) ? (n - J0) : NB2;
+    for (int j0 = J0; j0 < J0 + jb2; j0 += NB) {
+      const int jb = (J0 + jb2 - j0 < NB) ? (J0 + jb2 - j0) : NB;
+      const int m = n - j0;
+      const int G = m > NB ? (m - NB + (CHOL_PANEL_THREADS - NB) - 1) / (CHOL_PANEL_THREADS - NB) : 1;
+      chol_panel_kernel<T><<<G, CHOL_PANEL_THREADS, shm, s>>>(lower, m, jb, A + j0 + (size_t)j0 * lda, lda, d_info, j0);
+      count_launch();
+      if (int rc = update(j0 + jb, j0 + jb, J0 + jb2, j0, j0 + jb)) return rc;     // rest of the outer block
+    }
+    if (int rc = update(J0 + jb2, J0 + jb2, n, J0, J0 + jb2)) return rc;           // trailing matrix
+  }
+  JB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // Two-level right-looking Cholesky: outer panels of NB2 columns are factorised by the NB=32 routine, the
 // block column (row) below (right of) them is solved 32 columns at a time, and the trailing matrix gets ONE
 // rank-NB2 update per outer step through the tuned GEMM (DMMA for double / complex double) — NB2/32 times
@@ -1053,6 +1177,7 @@ int potrf_device(char uplo, int n, T *A, int lda, int *d_info, cudaStream_t s) {
   int NB2 = option("potrf.nb2");
   // measured (tools/time_lapack.py): single level wins below ~4096 (launch bound), two levels above
   if (NB2 <= 0) NB2 = (n >= 16384) ? 512 : (n >= 4096 ? 256 : n);
+  if (option("potrf.variant") <= 0) return potrf_panels<T>(uplo, n, A, lda, d_info, NB2, s);   // 1: separate potf2 / trsm kernels
   if (n <= NB2 + NB) { int rc = potrf_nb32<T>(lower, n, A, lda, d_info, 0, s); if (!rc) JB_CUDA(cudaGetLastError()); return rc; }
   for (int j0 = 0; j0 < n; j0 += NB2) {
     const int jb2 = (n - j0 < NB2) ? (n - j0) : NB2;
