@@ -1052,11 +1052,120 @@ static int apply_row_perm(int inverse, int n, int nrhs, const int *d_ipiv, T *B,
   return rc;
 }
 
+// ------------------------------------------------------------------ getrs for a few right-hand sides
+// The blocked path above costs ~4 launches per 32 rows whatever nrhs is (dgesv 512 with one right-hand side spent
+// 0.48 ms in it).  For a handful of right-hand sides one CTA per column does the whole solve: the column sits in
+// shared memory, thread 0 replays the interchanges on it, then 32-row blocks go forward through unit-lower L and back
+// through U — warp 0 solves the diagonal block (lane = row, the solved component broadcast by shuffle), all warps
+// subtract the block's contribution from the remaining rows with the factor streamed from L2, and the next diagonal
+// block is fetched while they do.  Same operations as ?getrs (x_i * (1/u_ii) like the blocked path).
+constexpr int GETRS_FUSED_THREADS = 512;
+template <typename T> __device__ __forceinline__ T shfl_T(T v, int src) {
+  if constexpr (Num<T>::cplx) { v.x = __shfl_sync(0xffffffffu, v.x, src); v.y = __shfl_sync(0xffffffffu, v.y, src); return v; }
+  else return __shfl_sync(0xffffffffu, v, src);
+}
+template <typename T>
+__global__ void __launch_bounds__(GETRS_FUSED_THREADS)
+getrs_fused_kernel(int n, const T *__restrict__ A, int lda, const int *__restrict__ ipiv, T *__restrict__ B, int ldb) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T *x = reinterpret_cast<T *>(smem_raw);
+  int *piv = reinterpret_cast<int *>(x + n);
+  __shared__ T Ms[NB][NB + 1];
+  __shared__ T xb[NB];
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  T *b = B + (size_t)blockIdx.x * ldb;
+  for (int i = tid; i < n; i += nt) { x[i] = b[i]; piv[i] = ipiv[i]; }
+  // diagonal block (r, c) of the factor at block offset j0, zero outside the matrix; two entries per thread
+  auto fetch = [&](int j0, T &e0, T &e1) {
+    const int r0 = tid & 31, c0 = tid >> 5, c1 = c0 + 16;
+    e0 = (j0 + r0 < n && j0 + c0 < n) ? A[(j0 + r0) + (size_t)(j0 + c0) * lda] : Num<T>::zero();
+    e1 = (j0 + r0 < n && j0 + c1 < n) ? A[(j0 + r0) + (size_t)(j0 + c1) * lda] : Num<T>::zero();
+  };
+  auto stash = [&](T e0, T e1) { Ms[tid & 31][tid >> 5] = e0; Ms[tid & 31][(tid >> 5) + 16] = e1; };
+  T e0, e1;
+  fetch(0, e0, e1);
+  __syncthreads();
+  if (tid == 0)
+    for (int k = 0; k < n; k++) {
+      const int p = piv[k] - 1;
+      if (p != k && p >= 0 && p < n) { const T t = x[k]; x[k] = x[p]; x[p] = t; }
+    }
+  stash(e0, e1);
+  __syncthreads();
+  const int nblk = (n + NB - 1) / NB;
+  // ---- forward: L y = P b, unit diagonal
+  for (int bi = 0; bi < nblk; bi++) {
+    const int j0 = bi * NB, jb = min(NB, n - j0);
+    if (warp == 0) {
+      T xl = lane < jb ? x[j0 + lane] : Num<T>::zero();
+#pragma unroll
+      for (int i = 0; i < NB; i++) {
+        const T xi = shfl_T<T>(xl, i);
+        if (lane > i) xl = Num<T>::msub(xl, Ms[lane][i], xi);
+      }
+      if (lane < jb) x[j0 + lane] = xl;
+      xb[lane] = lane < jb ? xl : Num<T>::zero();
+    }
+    if (bi + 1 < nblk) fetch(j0 + NB, e0, e1);
+    __syncthreads();
+    for (int r = j0 + NB + tid; r < n; r += nt) {
+      T acc = x[r];
+      const T *Ar = A + r + (size_t)j0 * lda;
+#pragma unroll 8
+      for (int i = 0; i < NB; i++) acc = Num<T>::msub(acc, Ar[(size_t)i * lda], xb[i]);
+      x[r] = acc;
+    }
+    if (bi + 1 < nblk) stash(e0, e1);
+    __syncthreads();
+  }
+  // ---- backward: U x = y
+  fetch((nblk - 1) * NB, e0, e1);
+  stash(e0, e1);
+  __syncthreads();
+  for (int bi = nblk - 1; bi >= 0; bi--) {
+    const int j0 = bi * NB, jb = min(NB, n - j0);
+    if (warp == 0) {
+      T xl = lane < jb ? x[j0 + lane] : Num<T>::zero();
+      const T rinv = lane < jb ? Num<T>::recip(Ms[lane][lane]) : Num<T>::zero();
+#pragma unroll
+      for (int i = NB - 1; i >= 0; i--) {
+        const T xi = shfl_T<T>(Num<T>::cmul(xl, rinv), i);
+        if (lane == i) xl = xi;
+        else if (lane < i) xl = Num<T>::msub(xl, Ms[lane][i], xi);
+      }
+      if (lane < jb) x[j0 + lane] = xl;
+      xb[lane] = lane < jb ? xl : Num<T>::zero();
+    }
+    if (bi > 0) fetch(j0 - NB, e0, e1);
+    __syncthreads();
+    for (int r = tid; r < j0; r += nt) {
+      T acc = x[r];
+      const T *Ar = A + r + (size_t)j0 * lda;
+      for (int i = 0; i < jb; i++) acc = Num<T>::msub(acc, Ar[(size_t)i * lda], xb[i]);
+      x[r] = acc;
+    }
+    if (bi > 0) stash(e0, e1);
+    __syncthreads();
+  }
+  for (int i = tid; i < n; i += nt) b[i] = x[i];
+}
+
 template <typename T>
 int getrs_device(char trans, int n, int nrhs, const T *A, int lda, const int *d_ipiv, T *B, int ldb, cudaStream_t s) {
   if (n <= 0 || nrhs <= 0) return 0;
   int rc;
   if (trans == 'N' || trans == 'n') {
+    // options: getrs.fused_max_nrhs (unset: 16, 0: never), getrs.fused_max_n (unset: 4096)
+    const int fused_nrhs = option("getrs.fused_max_nrhs") >= 0 ? option("getrs.fused_max_nrhs") : 16;
+    const int fused_n = option("getrs.fused_max_n") > 0 ? option("getrs.fused_max_n") : 4096;
+    if (nrhs <= fused_nrhs && n <= fused_n) {
+      const size_t shm = (size_t)n * (sizeof(T) + sizeof(int));
+      JB_CUDA(cudaFuncSetAttribute(getrs_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+      getrs_fused_kernel<T><<<nrhs, GETRS_FUSED_THREADS, shm, s>>>(n, A, lda, d_ipiv, B, ldb);
+      count_launch();
+      JB_CUDA(cudaGetLastError());
+      return 0;
+    }
     if ((rc = apply_row_perm<T>(0, n, nrhs, d_ipiv, B, ldb, s))) return rc;
     if ((rc = trsm_left_blocked<T>(1, 111, 1, n, nrhs, A, lda, B, ldb, s))) return rc;
     if ((rc = trsm_left_blocked<T>(0, 111, 0, n, nrhs, A, lda, B, ldb, s))) return rc;

@@ -100,6 +100,30 @@ def test_getrs_all_trans(gpu, orc, rng, t, trans):
 
 
 @pytest.mark.parametrize("t", TYPES)
+@pytest.mark.parametrize("n,nrhs", [(1, 1), (33, 2), (700, 1), (1100, 16)])
+def test_getrs_fused_and_blocked_paths(gpu, orc, rng, t, n, nrhs):
+    """Few right-hand sides take the one-CTA-per-column kernel, the rest the blocked trsm path: both against the oracle."""
+    from jalla_b200._lib import lib
+    if t in "cz" and n > 700:
+        n = 600
+    A = rand(rng, t, n, n); B = rand(rng, t, n, nrhs, n + 3)
+    LU = A.copy(order="F"); piv = np.zeros(n, np.int32)
+    assert orc.getrf(t, 102, n, n, LU, n, piv) == 0
+    Bo = B.copy(order="F")
+    assert orc.getrs(t, 102, "N", n, nrhs, LU, n, piv, Bo, n + 3) == 0
+    for fused in (None, 0):
+        Bg = B.copy(order="F")
+        if fused is not None:
+            lib.jb_set_option(b"getrs.fused_max_nrhs", fused)
+        try:
+            assert gpu.getrs(t, 102, "N", n, nrhs, LU, n, piv, Bg, n + 3) == 0
+        finally:
+            lib.jb_set_option(b"getrs.fused_max_nrhs", -1)
+        assert fro(Bg[:n] - Bo[:n]) / fro(Bo[:n]) <= 1e3 * n * EPS[t]
+        assert np.isnan(Bg[n:, :]).all()
+
+
+@pytest.mark.parametrize("t", TYPES)
 @pytest.mark.parametrize("n", [1, 31, 128, 300])
 def test_getri_invert(gpu, orc, rng, t, n):
     """unsafeInvert (Matrix.hs:763-776): getrf then getri."""
