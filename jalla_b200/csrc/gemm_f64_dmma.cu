@@ -226,6 +226,8 @@ static int launch(const CUtensorMap &ma, const CUtensorMap &mb, int m, int n, in
   // overlap it with other kernels — the NCCL panel broadcasts of the sharded GEMM — leave a few SMs free
   const int cap = option("gemm.max_ctas");
   if (cap > 0 && cap < grid) grid = cap;
+  const int tcap = tls().gemm_cta_cap;          // set by the look-ahead factorisations around their trailing update
+  if (tcap > 0 && tcap < grid) grid = tcap;
   dgemm_dmma_kernel<A_KM, B_KM><<<grid, THREADS, SMEM_BYTES, s>>>(ma, mb, m, n, k, alpha, beta, C, ldc, tri);
   count_launch();
   JB_CUDA(cudaGetLastError());

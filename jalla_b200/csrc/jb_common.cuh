@@ -127,6 +127,7 @@ struct ThreadState {
   cudaStream_t stream = nullptr;
   int err = 0;
   char msg[256] = {0};
+  int gemm_cta_cap = 0;     // > 0: the persistent DMMA GEMMs launched by this thread use at most this many CTAs (SMs)
 };
 ThreadState &tls();
 void set_error(int code, const char *fmt, ...);

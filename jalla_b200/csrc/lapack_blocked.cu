@@ -969,21 +969,74 @@ int getrf_device(int m, int n, T *A, int lda, int *d_ipiv, int *d_info, cudaStre
     rc = getrf_nb32<T>(m, n, A, lda, d_ipiv, d_info, 0, ctx, s);
   } else {
     const T minus1 = Num<T>::neg(Num<T>::one()), one = Num<T>::one();
+    // Look-ahead: the update of outer step J is split into the columns of block J+1 and the rest.  As soon as the
+    // first part is done, block J+1 is factorised on a second (higher-priority) stream while the main stream
+    // finishes the trailing update — the two touch disjoint columns.  The persistent DMMA GEMM owns every SM it
+    // runs on, so during the overlap it is capped to leave the panel kernels their CTAs (thread-local cap).
+    const bool lookahead = option("getrf.lookahead") != 0;
+    cudaStream_t s2 = nullptr;
+    cudaEvent_t ev_first = nullptr, ev_panel = nullptr;
+    if (lookahead) {
+      int lo = 0, hi = 0;
+      JB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      JB_CUDA(cudaStreamCreateWithPriority(&s2, cudaStreamNonBlocking, hi));
+      JB_CUDA(cudaEventCreateWithFlags(&ev_first, cudaEventDisableTiming));
+      JB_CUDA(cudaEventCreateWithFlags(&ev_panel, cudaEventDisableTiming));
+    }
+    // right-of-block work of outer step (J0, jb2) on columns [c0, c1): interchanges, U12 solve, rank-jb2 update
+    auto right_update = [&](int J0, int jb2, int c0, int c1, cudaStream_t st) -> int {
+      if (c1 <= c0) return 0;
+      int r = laswp_launch<T>(A, lda, c0, c1, d_ipiv, J0, J0 + jb2, 0, st);
+      if (!r) r = trsm_left_blocked<T>(1, 111, 1, jb2, c1 - c0, A + J0 + (size_t)J0 * lda, lda, A + J0 + (size_t)c0 * lda, lda, st);
+      const int mr = m - J0 - jb2;
+      if (!r && mr > 0)
+        r = gemm_device<T>(111, 111, mr, c1 - c0, jb2, minus1, A + (J0 + jb2) + (size_t)J0 * lda, lda,
+                           A + J0 + (size_t)c0 * lda, lda, one, A + (J0 + jb2) + (size_t)c0 * lda, lda, st, 0);
+      return r;
+    };
+    bool factored = false;                      // block at J0 already factorised by the previous step's look-ahead
     for (int J0 = 0; J0 < mn && !rc; J0 += NB2) {
       const int jb2 = (mn - J0 < NB2) ? (mn - J0) : NB2;
-      rc = getrf_nb32<T>(m - J0, jb2, A + J0 + (size_t)J0 * lda, lda, d_ipiv + J0, d_info, J0, ctx, s);
+      if (!factored)
+        rc = getrf_nb32<T>(m - J0, jb2, A + J0 + (size_t)J0 * lda, lda, d_ipiv + J0, d_info, J0, ctx, s);
+      factored = false;
       if (rc) break;
       if (J0 > 0) rc = laswp_launch<T>(A, lda, 0, J0, d_ipiv, J0, J0 + jb2, 0, s);
       if (rc) break;
-      const int nr = n - J0 - jb2;
-      if (nr > 0) {
-        rc = laswp_launch<T>(A, lda, J0 + jb2, n, d_ipiv, J0, J0 + jb2, 0, s);
-        if (!rc) rc = trsm_left_blocked<T>(1, 111, 1, jb2, nr, A + J0 + (size_t)J0 * lda, lda, A + J0 + (size_t)(J0 + jb2) * lda, lda, s);
-        const int mr = m - J0 - jb2;
-        if (!rc && mr > 0)
-          rc = gemm_device<T>(111, 111, mr, nr, jb2, minus1, A + (J0 + jb2) + (size_t)J0 * lda, lda,
-                              A + J0 + (size_t)(J0 + jb2) * lda, lda, one, A + (J0 + jb2) + (size_t)(J0 + jb2) * lda, lda, s, 0);
+      const int c0 = J0 + jb2;
+      if (n - c0 <= 0) break;
+      const int jn = (c0 < mn) ? ((mn - c0 < NB2) ? (mn - c0) : NB2) : 0;      // width of the next block
+      const int mr = m - c0;
+      if (lookahead && jn > 0 && mr > 0) {
+        rc = right_update(J0, jb2, c0, c0 + jn, s);
+        if (rc) break;
+        JB_CUDA(cudaEventRecord(ev_first, s));
+        JB_CUDA(cudaStreamWaitEvent(s2, ev_first, 0));
+        rc = getrf_nb32<T>(m - c0, jn, A + c0 + (size_t)c0 * lda, lda, d_ipiv + c0, d_info, c0, ctx, s2);
+        if (rc) break;
+        JB_CUDA(cudaEventRecord(ev_panel, s2));
+        // CTAs the panel phase needs at once: the cooperative panel grid (256 rows each) or one CTA
+        constexpr int MAXT = PanelMaxThreads<T>::value;
+        int need = mr > MAXT ? (mr + PANEL_MULTI_THREADS - 1) / PANEL_MULTI_THREADS : 1;
+        need += 8;                              // + room for its interchange / small-solve / small-GEMM launches
+        ThreadState &ts = tls();
+        const int saved_cap = ts.gemm_cta_cap;
+        // Measured: reserving 38 SMs pays at n = 8192 (43.0 -> 37.0 ms) but 70 SMs at n = 16384 cost more GEMM time
+        // than the panels hide (175 -> 201 ms).  Taller panels therefore run after the update, uncapped.
+        if (need <= 40) ts.gemm_cta_cap = nsm - need;
+        rc = right_update(J0, jb2, c0 + jn, n, s);
+        ts.gemm_cta_cap = saved_cap;
+        JB_CUDA(cudaStreamWaitEvent(s, ev_panel, 0));
+        factored = true;
+      } else {
+        rc = right_update(J0, jb2, c0, n, s);
       }
+    }
+    if (lookahead) {
+      // s has waited for everything s2 did; destruction is deferred by the runtime until the work has drained
+      cudaEventDestroy(ev_first);
+      cudaEventDestroy(ev_panel);
+      cudaStreamDestroy(s2);
     }
   }
   if (prof) {
@@ -1248,27 +1301,75 @@ static int potrf_panels(char uplo, int n, T *A, int lda, int *d_info, int NB2, c
   const size_t shm = (size_t)NB * CHOL_PANEL_THREADS * sizeof(T);
   JB_CUDA(cudaFuncSetAttribute(chol_panel_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
   // C[r0:, c0:c1] -= L[r0:, k0:k1] * L[c0:c1, k0:k1]^H in lower form (rows >= columns only), or its mirror image
-  auto update = [&](int r0, int c0, int c1, int k0, int k1) -> int {
+  auto update = [&](int r0, int c0, int c1, int k0, int k1, cudaStream_t st) -> int {
     const int mr = n - r0, nc = c1 - c0, kk = k1 - k0;
     if (mr <= 0 || nc <= 0) return 0;
     if (lower)
       return gemm_device<T>(111, tc, mr, nc, kk, minus1, A + r0 + (size_t)k0 * lda, lda, A + c0 + (size_t)k0 * lda, lda, one,
-                            A + r0 + (size_t)c0 * lda, lda, s, 'L');
+                            A + r0 + (size_t)c0 * lda, lda, st, 'L');
     return gemm_device<T>(tc, 111, nc, mr, kk, minus1, A + k0 + (size_t)c0 * lda, lda, A + k0 + (size_t)r0 * lda, lda, one,
-                          A + c0 + (size_t)r0 * lda, lda, s, 'U');
+                          A + c0 + (size_t)r0 * lda, lda, st, 'U');
   };
-  for (int J0 = 0; J0 < n; J0 += NB2) {
-    const int jb2 = (n - J0 < NB2) ? (n - J0) : NB2;
+  // the 32-column panels of outer block [J0, J0 + jb2) with the updates that stay inside the block
+  auto factor_block = [&](int J0, int jb2, cudaStream_t st) -> int {
     for (int j0 = J0; j0 < J0 + jb2; j0 += NB) {
       const int jb = (J0 + jb2 - j0 < NB) ? (J0 + jb2 - j0) : NB;
       const int m = n - j0;
       const int G = m > NB ? (m - NB + (CHOL_PANEL_THREADS - NB) - 1) / (CHOL_PANEL_THREADS - NB) : 1;
-      chol_panel_kernel<T><<<G, CHOL_PANEL_THREADS, shm, s>>>(lower, m, jb, A + j0 + (size_t)j0 * lda, lda, d_info, j0);
+      chol_panel_kernel<T><<<G, CHOL_PANEL_THREADS, shm, st>>>(lower, m, jb, A + j0 + (size_t)j0 * lda, lda, d_info, j0);
       count_launch();
-      if (int rc = update(j0 + jb, j0 + jb, J0 + jb2, j0, j0 + jb)) return rc;     // rest of the outer block
+      if (int rc = update(j0 + jb, j0 + jb, J0 + jb2, j0, j0 + jb, st)) return rc;
     }
-    if (int rc = update(J0 + jb2, J0 + jb2, n, J0, J0 + jb2)) return rc;           // trailing matrix
+    return 0;
+  };
+  // Look-ahead as in getrf_device: the trailing update is split into the next block's columns and the rest, and the
+  // next block is factorised on a second, higher-priority stream while the main stream finishes the rest.  The panel
+  // CTAs are independent (no co-residency needed), so a fixed 16 SMs are kept free of the persistent DMMA GEMM.
+  const bool lookahead = option("potrf.lookahead") != 0 && n > NB2 + NB;
+  cudaStream_t s2 = nullptr;
+  cudaEvent_t ev_first = nullptr, ev_panel = nullptr;
+  if (lookahead) {
+    int lo = 0, hi = 0;
+    JB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    JB_CUDA(cudaStreamCreateWithPriority(&s2, cudaStreamNonBlocking, hi));
+    JB_CUDA(cudaEventCreateWithFlags(&ev_first, cudaEventDisableTiming));
+    JB_CUDA(cudaEventCreateWithFlags(&ev_panel, cudaEventDisableTiming));
   }
+  int rc = 0;
+  bool factored = false;
+  for (int J0 = 0; J0 < n && !rc; J0 += NB2) {
+    const int jb2 = (n - J0 < NB2) ? (n - J0) : NB2;
+    if (!factored) rc = factor_block(J0, jb2, s);
+    factored = false;
+    if (rc) break;
+    const int c0 = J0 + jb2;
+    if (c0 >= n) break;
+    const int jn = (n - c0 < NB2) ? (n - c0) : NB2;
+    if (lookahead && c0 + jn < n) {
+      rc = update(c0, c0, c0 + jn, J0, c0, s);
+      if (rc) break;
+      JB_CUDA(cudaEventRecord(ev_first, s));
+      JB_CUDA(cudaStreamWaitEvent(s2, ev_first, 0));
+      rc = factor_block(c0, jn, s2);
+      if (rc) break;
+      JB_CUDA(cudaEventRecord(ev_panel, s2));
+      ThreadState &ts = tls();
+      const int saved_cap = ts.gemm_cta_cap;
+      ts.gemm_cta_cap = num_sms() - 16;
+      rc = update(c0 + jn, c0 + jn, n, J0, c0, s);
+      ts.gemm_cta_cap = saved_cap;
+      JB_CUDA(cudaStreamWaitEvent(s, ev_panel, 0));
+      factored = true;
+    } else {
+      rc = update(c0, c0, n, J0, c0, s);
+    }
+  }
+  if (lookahead) {
+    cudaEventDestroy(ev_first);
+    cudaEventDestroy(ev_panel);
+    cudaStreamDestroy(s2);
+  }
+  if (rc) return rc;
   JB_CUDA(cudaGetLastError());
   return 0;
 }
