@@ -75,4 +75,9 @@ inline int make_map_f64(CUtensorMap *map, const void *ptr, long rows, long cols,
 }
 
 }  // namespace dmma
+// Asynchronous L2 prefetch of `bytes` (multiple of 16) at a 16-byte aligned global address.
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 }  // namespace jb
