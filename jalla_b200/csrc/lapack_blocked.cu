@@ -820,6 +820,31 @@ struct PanelCtx {
   PanelLLScratch ll{};
   bool have_ll = false;
 };
+// Scoped thread-local CTA cap for the persistent DMMA GEMMs (restored on every exit path).
+struct GemmCapScope {
+  int saved;
+  explicit GemmCapScope(int cap) : saved(tls().gemm_cta_cap) { if (cap > 0) tls().gemm_cta_cap = cap; }
+  ~GemmCapScope() { tls().gemm_cta_cap = saved; }
+};
+// Second stream + events of a look-ahead factorisation, released on every exit path (destruction of a stream or
+// event with work pending is deferred by the runtime until that work has drained).
+struct LookaheadStreams {
+  cudaStream_t s2 = nullptr;
+  cudaEvent_t ev_first = nullptr, ev_panel = nullptr;
+  int open() {
+    int lo = 0, hi = 0;
+    JB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    JB_CUDA(cudaStreamCreateWithPriority(&s2, cudaStreamNonBlocking, hi));
+    JB_CUDA(cudaEventCreateWithFlags(&ev_first, cudaEventDisableTiming));
+    JB_CUDA(cudaEventCreateWithFlags(&ev_panel, cudaEventDisableTiming));
+    return 0;
+  }
+  ~LookaheadStreams() {
+    if (ev_first) cudaEventDestroy(ev_first);
+    if (ev_panel) cudaEventDestroy(ev_panel);
+    if (s2) cudaStreamDestroy(s2);
+  }
+};
 // Tags of the flagged-word exchange must never repeat on memory a previous launch may have left behind.
 static unsigned next_panel_tag() {
   static std::atomic<unsigned> seq{1};
@@ -963,7 +988,9 @@ int getrf_device(int m, int n, T *A, int lda, int *d_ipiv, int *d_info, cudaStre
   }
   int NB2 = option("getrf.nb2");
   // measured (tools/time_nb2.py): 16384: 212.8 / 185.7 / 178.2 / 175.4 ms for 128 / 256 / 384 / 512; 8192: 46.6 / 43.9 / 43.6 / 43.2
-  if (NB2 <= 0) NB2 = (mn >= 8192) ? 512 : (mn >= 4096 ? 256 : mn);
+  // with look-ahead (tools/time_nb2_potrf.py): 4096: 13.8 / 14.5 / 14.6 ms for 128 / 256 / 512; 8192: 39.7 / 37.3 / 36.9;
+  // 16384: 181.7 / 165.2 / 158.5; 2048 stays single level (5.6 ms against 6.5)
+  if (NB2 <= 0) NB2 = (mn >= 8192) ? 512 : (mn >= 4096 ? 128 : mn);
   int rc = 0;
   if (mn <= NB2 + NB) {
     rc = getrf_nb32<T>(m, n, A, lda, d_ipiv, d_info, 0, ctx, s);
@@ -974,15 +1001,10 @@ int getrf_device(int m, int n, T *A, int lda, int *d_ipiv, int *d_info, cudaStre
     // finishes the trailing update — the two touch disjoint columns.  The persistent DMMA GEMM owns every SM it
     // runs on, so during the overlap it is capped to leave the panel kernels their CTAs (thread-local cap).
     const bool lookahead = option("getrf.lookahead") != 0;
-    cudaStream_t s2 = nullptr;
-    cudaEvent_t ev_first = nullptr, ev_panel = nullptr;
-    if (lookahead) {
-      int lo = 0, hi = 0;
-      JB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-      JB_CUDA(cudaStreamCreateWithPriority(&s2, cudaStreamNonBlocking, hi));
-      JB_CUDA(cudaEventCreateWithFlags(&ev_first, cudaEventDisableTiming));
-      JB_CUDA(cudaEventCreateWithFlags(&ev_panel, cudaEventDisableTiming));
-    }
+    LookaheadStreams la;
+    if (lookahead) if (int r = la.open()) { ws_free(scratch, s); ws_free(scratch_ll, s); return r; }
+    cudaStream_t s2 = la.s2;
+    cudaEvent_t ev_first = la.ev_first, ev_panel = la.ev_panel;
     // right-of-block work of outer step (J0, jb2) on columns [c0, c1): interchanges, U12 solve, rank-jb2 update
     auto right_update = [&](int J0, int jb2, int c0, int c1, cudaStream_t st) -> int {
       if (c1 <= c0) return 0;
@@ -1019,24 +1041,21 @@ int getrf_device(int m, int n, T *A, int lda, int *d_ipiv, int *d_info, cudaStre
         constexpr int MAXT = PanelMaxThreads<T>::value;
         int need = mr > MAXT ? (mr + PANEL_MULTI_THREADS - 1) / PANEL_MULTI_THREADS : 1;
         need += 8;                              // + room for its interchange / small-solve / small-GEMM launches
-        ThreadState &ts = tls();
-        const int saved_cap = ts.gemm_cta_cap;
         // Measured: reserving 38 SMs pays at n = 8192 (43.0 -> 37.0 ms) but 70 SMs at n = 16384 cost more GEMM time
         // than the panels hide (175 -> 201 ms).  Taller panels therefore run after the update, uncapped.
-        if (need <= 40) ts.gemm_cta_cap = nsm - need;
-        rc = right_update(J0, jb2, c0 + jn, n, s);
-        ts.gemm_cta_cap = saved_cap;
+        {
+          GemmCapScope cap(need <= 40 ? nsm - need : 0);
+          rc = right_update(J0, jb2, c0 + jn, n, s);
+        }
         JB_CUDA(cudaStreamWaitEvent(s, ev_panel, 0));
         factored = true;
       } else {
         rc = right_update(J0, jb2, c0, n, s);
       }
     }
-    if (lookahead) {
-      // s has waited for everything s2 did; destruction is deferred by the runtime until the work has drained
-      cudaEventDestroy(ev_first);
-      cudaEventDestroy(ev_panel);
-      cudaStreamDestroy(s2);
+    if (lookahead) {              // whatever path left the loop: nothing of the second stream outlives the call's stream order
+      cudaEventRecord(ev_panel, s2);
+      cudaStreamWaitEvent(s, ev_panel, 0);
     }
   }
   if (prof) {
@@ -1326,15 +1345,10 @@ static int potrf_panels(char uplo, int n, T *A, int lda, int *d_info, int NB2, c
   // next block is factorised on a second, higher-priority stream while the main stream finishes the rest.  The panel
   // CTAs are independent (no co-residency needed), so a fixed 16 SMs are kept free of the persistent DMMA GEMM.
   const bool lookahead = option("potrf.lookahead") != 0 && n > NB2 + NB;
-  cudaStream_t s2 = nullptr;
-  cudaEvent_t ev_first = nullptr, ev_panel = nullptr;
-  if (lookahead) {
-    int lo = 0, hi = 0;
-    JB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    JB_CUDA(cudaStreamCreateWithPriority(&s2, cudaStreamNonBlocking, hi));
-    JB_CUDA(cudaEventCreateWithFlags(&ev_first, cudaEventDisableTiming));
-    JB_CUDA(cudaEventCreateWithFlags(&ev_panel, cudaEventDisableTiming));
-  }
+  LookaheadStreams la;
+  if (lookahead) if (int r = la.open()) return r;
+  cudaStream_t s2 = la.s2;
+  cudaEvent_t ev_first = la.ev_first, ev_panel = la.ev_panel;
   int rc = 0;
   bool factored = false;
   for (int J0 = 0; J0 < n && !rc; J0 += NB2) {
@@ -1353,11 +1367,10 @@ static int potrf_panels(char uplo, int n, T *A, int lda, int *d_info, int NB2, c
       rc = factor_block(c0, jn, s2);
       if (rc) break;
       JB_CUDA(cudaEventRecord(ev_panel, s2));
-      ThreadState &ts = tls();
-      const int saved_cap = ts.gemm_cta_cap;
-      ts.gemm_cta_cap = num_sms() - 16;
-      rc = update(c0 + jn, c0 + jn, n, J0, c0, s);
-      ts.gemm_cta_cap = saved_cap;
+      {
+        GemmCapScope cap(num_sms() - 16);
+        rc = update(c0 + jn, c0 + jn, n, J0, c0, s);
+      }
       JB_CUDA(cudaStreamWaitEvent(s, ev_panel, 0));
       factored = true;
     } else {
@@ -1365,9 +1378,8 @@ static int potrf_panels(char uplo, int n, T *A, int lda, int *d_info, int NB2, c
     }
   }
   if (lookahead) {
-    cudaEventDestroy(ev_first);
-    cudaEventDestroy(ev_panel);
-    cudaStreamDestroy(s2);
+    cudaEventRecord(ev_panel, s2);
+    cudaStreamWaitEvent(s, ev_panel, 0);
   }
   if (rc) return rc;
   JB_CUDA(cudaGetLastError());
@@ -1386,7 +1398,9 @@ int potrf_device(char uplo, int n, T *A, int lda, int *d_info, cudaStream_t s) {
   const int tc = Num<T>::cplx ? 113 : 112;
   int NB2 = option("potrf.nb2");
   // measured (tools/time_lapack.py): single level wins below ~4096 (launch bound), two levels above
-  if (NB2 <= 0) NB2 = (n >= 16384) ? 512 : (n >= 4096 ? 256 : n);
+  // with look-ahead (tools/time_nb2_potrf.py, ms for 128 / 256 / 512): 2048: 2.23 / 2.18 / 2.35 (single level 2.36);
+  // 4096: 4.67 / 4.89 / 5.14; 8192: 15.5 / 13.8 / 14.5; 16384: 81.5 / 68.4 / 64.3
+  if (NB2 <= 0) NB2 = (n >= 16384) ? 512 : (n >= 8192 ? 256 : (n >= 2048 ? 128 : n));
   if (option("potrf.variant") <= 0) return potrf_panels<T>(uplo, n, A, lda, d_info, NB2, s);   // 1: separate potf2 / trsm kernels
   if (n <= NB2 + NB) { int rc = potrf_nb32<T>(lower, n, A, lda, d_info, 0, s); if (!rc) JB_CUDA(cudaGetLastError()); return rc; }
   for (int j0 = 0; j0 < n; j0 += NB2) {
