@@ -1397,8 +1397,7 @@ int potrf_device(char uplo, int n, T *A, int lda, int *d_info, cudaStream_t s) {
   const T minus1 = Num<T>::neg(Num<T>::one()), one = Num<T>::one();
   const int tc = Num<T>::cplx ? 113 : 112;
   int NB2 = option("potrf.nb2");
-  // measured (tools/time_lapack.py): single level wins below ~4096 (launch bound), two levels above
-  // with look-ahead (tools/time_nb2_potrf.py, ms for 128 / 256 / 512): 2048: 2.23 / 2.18 / 2.35 (single level 2.36);
+  // outer block width, measured with look-ahead (tools/time_nb2_potrf.py, ms for 128 / 256 / 512): 2048: 2.23 / 2.18 / 2.35 (single level 2.36);
   // 4096: 4.67 / 4.89 / 5.14; 8192: 15.5 / 13.8 / 14.5; 16384: 81.5 / 68.4 / 64.3
   if (NB2 <= 0) NB2 = (n >= 16384) ? 512 : (n >= 8192 ? 256 : (n >= 2048 ? 128 : n));
   if (option("potrf.variant") <= 0) return potrf_panels<T>(uplo, n, A, lda, d_info, NB2, s);   // 1: separate potf2 / trsm kernels
