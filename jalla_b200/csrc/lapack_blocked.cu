@@ -482,7 +482,8 @@ lu_panel_reg_kernel(int pm, int jb, T *__restrict__ Pg, int ldg, int *__restrict
 constexpr int LASWP_THREADS = 256, LASWP_MAXCHUNK = 16, LASWP_COLS_PER_WARP = 4;
 template <typename T>
 __global__ void __launch_bounds__(LASWP_THREADS)
-laswp_kernel(T *__restrict__ A, int lda, int c0, int c1, const int *__restrict__ ipiv, int k0, int k1, int row_base) {
+laswp_kernel(T *__restrict__ A, int lda, int c0, int c1, const int *__restrict__ ipiv, int k0, int k1, int row_base,
+             int tri) {
   __shared__ int s_rows[LASWP_MAXCHUNK][64], s_cur[LASWP_MAXCHUNK][64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = LASWP_THREADS / 32;
   const int nchunk = (k1 - k0 + 31) / 32;
@@ -510,7 +511,10 @@ laswp_kernel(T *__restrict__ A, int lda, int c0, int c1, const int *__restrict__
   __syncthreads();
   const int col_first = c0 + (blockIdx.x * nwarp + warp) * LASWP_COLS_PER_WARP;
   if (col_first >= c1) return;
-  for (int q = 0; q < nchunk; q++) {
+  // tri: column c only takes the interchanges from the end of its own 32-column block on (the deferred left-hand
+  // interchanges of a panel sweep; k0 and c0 are multiples of 32 there, so the start is uniform across the warp)
+  const int q_first = tri ? max(0, ((col_first / NB + 1) * NB - k0) / 32) : 0;
+  for (int q = q_first; q < nchunk; q++) {
     // slot i finally holds what slot s_cur[i] held before the chunk
     const int src_lo = s_cur[q][lane], src_hi = s_cur[q][32 + lane];
     const bool mv_lo = src_lo != lane, mv_hi = src_hi != 32 + lane;
@@ -541,15 +545,99 @@ laswp_kernel(T *__restrict__ A, int lda, int c0, int c1, const int *__restrict__
 }
 
 template <typename T>
-static int laswp_launch(T *A, int lda, int c0, int c1, const int *d_ipiv, int k0, int k1, int row_base, cudaStream_t s) {
+static int laswp_launch(T *A, int lda, int c0, int c1, const int *d_ipiv, int k0, int k1, int row_base, cudaStream_t s,
+                        int tri = 0) {
   if (c1 <= c0 || k1 <= k0) return 0;
   const int cols_per_cta = (LASWP_THREADS / 32) * LASWP_COLS_PER_WARP;
   for (int q0 = k0; q0 < k1; q0 += 32 * LASWP_MAXCHUNK) {
     const int q1 = (k1 - q0 < 32 * LASWP_MAXCHUNK) ? k1 : q0 + 32 * LASWP_MAXCHUNK;
-    laswp_kernel<T><<<(c1 - c0 + cols_per_cta - 1) / cols_per_cta, LASWP_THREADS, 0, s>>>(A, lda, c0, c1, d_ipiv, q0, q1, row_base);
+    // tri: columns whose block ends at or after q1 have nothing to take from this launch
+    const int cend = tri ? min(c1, ((q1 - 1) / NB) * NB) : c1;
+    if (cend <= c0) continue;
+    laswp_kernel<T><<<(cend - c0 + cols_per_cta - 1) / cols_per_cta, LASWP_THREADS, 0, s>>>(A, lda, c0, cend, d_ipiv, q0, q1, row_base, tri);
     count_launch();
   }
   return 0;
+}
+
+template <typename T> __device__ __forceinline__ T shfl_T(T v, int src) {
+  if constexpr (Num<T>::cplx) { v.x = __shfl_sync(0xffffffffu, v.x, src); v.y = __shfl_sync(0xffffffffu, v.y, src); return v; }
+  else return __shfl_sync(0xffffffffu, v, src);
+}
+// Interchanges of one panel applied to the columns right of it AND the unit-lower solve of the panel's block row
+// against the diagonal block, in one launch (they touch the same columns; separately they were two launch-bound
+// kernels per panel step).  Same permutation scheme as laswp_kernel for the <= 32 interchanges k0..k1; the warp that
+// owns a column then has the block row in its lanes (lane = row k0 + lane) and solves L11 x = b by shuffles, four
+// columns interleaved.  L11 = A[k0.., k0..] (unit diagonal, strictly lower part used).
+template <typename T>
+__global__ void __launch_bounds__(LASWP_THREADS)
+laswp_trsm_kernel(T *__restrict__ A, int lda, int c0, int c1, const int *__restrict__ ipiv, int k0, int k1, int row_base) {
+  __shared__ int s_rows[64], s_cur[64];
+  __shared__ T Ms[NB][NB + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = LASWP_THREADS / 32;
+  const int np = k1 - k0;
+  for (int e = threadIdx.x; e < NB * NB; e += LASWP_THREADS) {
+    const int r = e % NB, c = e / NB;
+    Ms[r][c] = (r < np && c < r) ? A[(k0 + r) + (size_t)(k0 + c) * lda] : Num<T>::zero();
+  }
+  if (warp == 0) {
+    int p = -1 - lane, slot = lane;
+    if (lane < np) {
+      p = ipiv[k0 + lane] - 1 - row_base;
+      slot = (p >= k0 && p < k0 + 32) ? p - k0 : -1;
+    }
+    const unsigned same = __match_any_sync(0xffffffffu, p);
+    if (slot < 0) slot = 32 + (__ffs(same) - 1);
+    s_rows[lane] = k0 + lane;
+    s_rows[32 + lane] = p;
+    s_cur[lane] = lane;
+    s_cur[32 + lane] = 32 + lane;
+    __syncwarp();
+    for (int k = 0; k < np; k++) {
+      const int b = __shfl_sync(0xffffffffu, slot, k);
+      if (lane == 0) { const int t = s_cur[k]; s_cur[k] = s_cur[b]; s_cur[b] = t; }
+    }
+  }
+  __syncthreads();
+  const int col_first = c0 + (blockIdx.x * nwarp + warp) * LASWP_COLS_PER_WARP;
+  if (col_first >= c1) return;
+  const int src_lo = s_cur[lane], src_hi = s_cur[32 + lane];
+  const bool mv_hi = src_hi != 32 + lane;
+  const int rs_lo = s_rows[src_lo], rs_hi = s_rows[src_hi];
+  const int rd_hi = s_rows[32 + lane];
+  const bool in_rows = lane < np;                       // slots >= np of a ragged last panel are other rows: untouched
+  T x[LASWP_COLS_PER_WARP], v_hi[LASWP_COLS_PER_WARP];
+#pragma unroll
+  for (int j = 0; j < LASWP_COLS_PER_WARP; j++) {
+    const int c = col_first + j;
+    x[j] = Num<T>::zero();
+    if (c < c1) {
+      const T *col = A + (size_t)c * lda;
+      if (in_rows || src_lo != lane) x[j] = col[rs_lo];   // what ends up in row k0 + lane
+      if (mv_hi) v_hi[j] = col[rs_hi];
+    }
+  }
+  __syncwarp();                                         // every lane has read before any lane overwrites
+  // unit-lower forward substitution, lane = row; rows >= np carry values that no lane below them uses (Ms is zero there)
+#pragma unroll
+  for (int i = 0; i < NB; i++) {
+    if (i < np) {
+#pragma unroll
+      for (int j = 0; j < LASWP_COLS_PER_WARP; j++) {
+        const T xi = shfl_T<T>(x[j], i);
+        if (lane > i && in_rows) x[j] = Num<T>::msub(x[j], Ms[lane][i], xi);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < LASWP_COLS_PER_WARP; j++) {
+    const int c = col_first + j;
+    if (c < c1) {
+      T *col = A + (size_t)c * lda;
+      if (in_rows || src_lo != lane) col[k0 + lane] = x[j];
+      if (mv_hi) col[rd_hi] = v_hi[j];
+    }
+  }
 }
 
 // ------------------------------------------------------------------ small triangular solves
@@ -911,15 +999,13 @@ static int getrf_nb32(int m, int n, T *A, int lda, int *d_ipiv, int *d_info, int
                                                                 row_base + j0, use_smem);
       count_launch();
     }
-    // interchange the columns of this block left and right of the panel
-    if (j0 > 0)
-      if (int rc = laswp_launch<T>(A, lda, 0, j0, d_ipiv, j0, j0 + jb, row_base, s)) return rc;
+    // The columns right of the panel take its interchanges and the block-row solve in one launch; the columns left
+    // of it (finished L, read by nothing later in this sweep) take all their interchanges in one pass at the end.
     const int nr = n - j0 - jb;
     if (nr > 0) {
-      if (int rc = laswp_launch<T>(A, lda, j0 + jb, n, d_ipiv, j0, j0 + jb, row_base, s)) return rc;
-      int blocks = (nr + 7) / 8; if (blocks > 4 * nsm) blocks = 4 * nsm;
-      trsm_small_left_kernel<T><<<blocks, 256, 0, s>>>(1, 1, 111, jb, nr, A + j0 + (size_t)j0 * lda, lda,
-                                                       A + j0 + (size_t)(j0 + jb) * lda, lda, nullptr);
+      const int cols_per_cta = (LASWP_THREADS / 32) * LASWP_COLS_PER_WARP;
+      laswp_trsm_kernel<T><<<(nr + cols_per_cta - 1) / cols_per_cta, LASWP_THREADS, 0, s>>>(A, lda, j0 + jb, n, d_ipiv, j0, j0 + jb,
+                                                                                         row_base);
       count_launch();
       const int mr = m - j0 - jb;
       if (mr > 0) {
@@ -930,6 +1016,8 @@ static int getrf_nb32(int m, int n, T *A, int lda, int *d_ipiv, int *d_info, int
       }
     }
   }
+  if (mn > NB)
+    if (int rc = laswp_launch<T>(A, lda, 0, ((mn - 1) / NB) * NB, d_ipiv, NB, mn, row_base, s, 1)) return rc;
   return 0;
 }
 
@@ -1132,10 +1220,6 @@ static int apply_row_perm(int inverse, int n, int nrhs, const int *d_ipiv, T *B,
 // subtract the block's contribution from the remaining rows with the factor streamed from L2, and the next diagonal
 // block is fetched while they do.  Same operations as ?getrs (x_i * (1/u_ii) like the blocked path).
 constexpr int GETRS_FUSED_THREADS = 512;
-template <typename T> __device__ __forceinline__ T shfl_T(T v, int src) {
-  if constexpr (Num<T>::cplx) { v.x = __shfl_sync(0xffffffffu, v.x, src); v.y = __shfl_sync(0xffffffffu, v.y, src); return v; }
-  else return __shfl_sync(0xffffffffu, v, src);
-}
 template <typename T>
 __global__ void __launch_bounds__(GETRS_FUSED_THREADS)
 getrs_fused_kernel(int n, const T *__restrict__ A, int lda, const int *__restrict__ ipiv, T *__restrict__ B, int ldb) {
