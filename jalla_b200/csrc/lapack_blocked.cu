@@ -1201,7 +1201,11 @@ static int apply_row_perm(int inverse, int n, int nrhs, const int *d_ipiv, T *B,
   T *W = nullptr;
   if (int rc = ws_alloc((void **)&perm, sizeof(int) * (size_t)n, s)) return rc;
   if (int rc = ws_alloc((void **)&W, sizeof(T) * (size_t)n * nrhs, s)) { ws_free(perm, s); return rc; }
-  const int perm_smem = (size_t)n * 2 * sizeof(int) <= 48 * 1024;
+  // the swap chain is n dependent steps: keep it in shared memory (opt-in size) up to n = 25600 before falling back
+  // to global memory, where every step is two dependent round trips
+  const int perm_smem = (size_t)n * 2 * sizeof(int) <= 200 * 1024;
+  if (perm_smem)
+    JB_CUDA(cudaFuncSetAttribute(perm_from_ipiv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   perm_from_ipiv_kernel<<<1, 256, perm_smem ? (size_t)n * 2 * sizeof(int) : 0, s>>>(n, d_ipiv, perm, perm_smem);
   dim3 grid((unsigned)min((n + 255) / 256, 1024), (unsigned)min(nrhs, 4096));
   permute_rows_kernel<T><<<grid, 256, 0, s>>>(inverse, n, nrhs, perm, B, ldb, W, n);
