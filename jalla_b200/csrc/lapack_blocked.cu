@@ -777,16 +777,23 @@ potf2_block_kernel(int lower, int jb, T *__restrict__ A, int lda, int *info, int
 // shared memory), but without a pivot search the only thing a column step needs from another thread is row c of
 // the diagonal block, scaled: u[j] = conj(L[c+j][c]).  Warp 0 of EVERY CTA carries the <= 32 diagonal-block rows
 // redundantly (mirrored to full Hermitian rows on load, only the stored triangle is read), so CTAs never talk to
-// each other and the grid needs no co-residency: CTA g owns rows 32 + g*(NT-32) ... and CTA 0 alone writes the
-// diagonal block back.  Row c's owner posts its scaled row before the column's single barrier (double buffered by
+// each other and the grid needs no co-residency: CTA g owns rows 32 + g*(NT-32) ... and the CTA that finishes last
+// writes the diagonal block back.  Row c's owner posts its scaled row before the column's single barrier (double buffered by
 // column parity).  Arithmetic per entry is potf2's: s = sqrt(d), l = a * (1/s), a -= l * conj(l').
 // `lower == 0` runs the same code on the conjugate-transposed addressing (the panel is then a block row of U).
 // info = first non-positive (or NaN) pivot, 1-based + off; the panel is then left partially factored like ?potf2.
 constexpr int CHOL_PANEL_THREADS = 256;
 template <typename T>
 __global__ void __launch_bounds__(CHOL_PANEL_THREADS, 1)
-chol_panel_kernel(int lower, int m, int jb, T *__restrict__ P, int lda, int *info, int off) {
-  if (*info) return;
+chol_panel_kernel(int lower, int m, int jb, T *__restrict__ P, int lda, int *info, int off, int *done_count) {
+  __shared__ int s_skip;                                // one read per CTA: info may be set by this very launch
+  if (threadIdx.x == 0) s_skip = *info;
+  __syncthreads();
+  if (s_skip) {
+    // an earlier panel failed: nothing to do, but the completion count (see the end of the kernel) stays consistent
+    if (threadIdx.x == 0 && atomicAdd(done_count, 1) == (int)gridDim.x - 1) *done_count = 0;
+    return;
+  }
   using R = typename Num<T>::R;
   using Pair = PanelPair<T>;
   constexpr int NT = CHOL_PANEL_THREADS;
@@ -797,7 +804,6 @@ chol_panel_kernel(int lower, int m, int jb, T *__restrict__ P, int lda, int *inf
   const int tid = threadIdx.x, warp = tid >> 5;
   const int row = warp == 0 ? tid : NB + blockIdx.x * (NT - NB) + (tid - NB);
   const bool live = row < m;
-  const bool writer = live && (warp != 0 || blockIdx.x == 0);
   auto at = [&](int r, int j) -> T * { return lower ? P + r + (size_t)j * lda : P + j + (size_t)r * lda; };
   T a[NB];
 #pragma unroll
@@ -841,6 +847,17 @@ chol_panel_kernel(int lower, int m, int jb, T *__restrict__ P, int lda, int *inf
     a[NB - 1] = Num<T>::zero();
   }
   if (failed_at >= 0 && blockIdx.x == 0 && tid == 0) *info = off + failed_at + 1;
+  // Every CTA holds the factorised diagonal block (bit-identical), but it must not reach memory while a CTA of a
+  // later wave can still load the original: the grid need not be co-resident (large m, or SMs shared with the
+  // look-ahead's trailing update).  So the CTA that finishes LAST writes it — by then every CTA has consumed its loads.
+  __shared__ int s_last;
+  __syncthreads();
+  if (tid == 0) {
+    s_last = atomicAdd(done_count, 1) == (int)gridDim.x - 1;
+    if (s_last) *done_count = 0;                        // ready for the next launch
+  }
+  __syncthreads();
+  const bool writer = live && (warp != 0 || s_last);
   if (!writer) return;
   if (failed_at >= 0) {
     // columns [0, failed_at) are final; park the partially updated rest (a[k] = column failed_at + k) next to them
@@ -1407,6 +1424,10 @@ static int potrf_panels(char uplo, int n, T *A, int lda, int *d_info, int NB2, c
   const int tc = Num<T>::cplx ? 113 : 112;
   const size_t shm = (size_t)NB * CHOL_PANEL_THREADS * sizeof(T);
   JB_CUDA(cudaFuncSetAttribute(chol_panel_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+  int *d_count = nullptr;                              // completion counter of the panel launches (self-resetting)
+  if (int r = ws_alloc((void **)&d_count, sizeof(int), s)) return r;
+  struct CountFree { int *p; cudaStream_t st; ~CountFree() { ws_free(p, st); } } count_free{d_count, s};
+  JB_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), s));
   // C[r0:, c0:c1] -= L[r0:, k0:k1] * L[c0:c1, k0:k1]^H in lower form (rows >= columns only), or its mirror image
   auto update = [&](int r0, int c0, int c1, int k0, int k1, cudaStream_t st) -> int {
     const int mr = n - r0, nc = c1 - c0, kk = k1 - k0;
@@ -1423,7 +1444,7 @@ static int potrf_panels(char uplo, int n, T *A, int lda, int *d_info, int NB2, c
       const int jb = (J0 + jb2 - j0 < NB) ? (J0 + jb2 - j0) : NB;
       const int m = n - j0;
       const int G = m > NB ? (m - NB + (CHOL_PANEL_THREADS - NB) - 1) / (CHOL_PANEL_THREADS - NB) : 1;
-      chol_panel_kernel<T><<<G, CHOL_PANEL_THREADS, shm, st>>>(lower, m, jb, A + j0 + (size_t)j0 * lda, lda, d_info, j0);
+      chol_panel_kernel<T><<<G, CHOL_PANEL_THREADS, shm, st>>>(lower, m, jb, A + j0 + (size_t)j0 * lda, lda, d_info, j0, d_count);
       count_launch();
       if (int rc = update(j0 + jb, j0 + jb, J0 + jb2, j0, j0 + jb, st)) return rc;
     }
