@@ -20,7 +20,7 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
     "-Xptxas", "-v",
-]
+] + os.environ.get("JB_NVCC_EXTRA", "").split()     # e.g. -DJB_LU32_ABLATIONS for tools/time_lu32.py's profiling variants
 
 
 def _sources():

@@ -31,6 +31,14 @@ class Dev:
         lib.jb_free(self.ptr)
 
 
+def assert_same_bits(x, y):
+    """Bit-identical except that any NaN matches any NaN (x86 and the GPU propagate different NaN payloads)."""
+    x = np.ascontiguousarray(x, dtype=np.float64); y = np.ascontiguousarray(y, dtype=np.float64)
+    nx, ny = np.isnan(x), np.isnan(y)
+    np.testing.assert_array_equal(nx, ny)
+    np.testing.assert_array_equal(np.where(nx, 0, x.view(np.int64)), np.where(ny, 0, y.view(np.int64)))
+
+
 def batch_rand(rng, t, batch, n, cols=None, lo=-1.0, hi=1.0):
     cols = n if cols is None else cols
     a = rng.uniform(lo, hi, (batch, cols, n))
@@ -137,6 +145,63 @@ def test_potrf_potrs_batched(orc, rng, t, uplo, n):
         else:
             assert fro(F[i][tri] - So[tri]) <= 50 * n * EPS[t] * fro(So[tri])
         assert fro(X[i] - Bo) <= 1e3 * n * EPS[t] * fro(Bo)
+
+
+@pytest.mark.parametrize("variant", [30, 31, 7, 6, 17, 16])
+def test_lu32_fast_kernels_special_values_and_strides(orc, rng, variant):
+    """Every shape of the tuned 32x32 Double kernels (jb_set_option lu32.variant) against the oracle, bit for bit, on a
+    batch that mixes generic systems with everything the fast path must hand to the exact routine: exact ties (integer
+    matrices), a zero column (info > 0), NaN and Inf entries (NaNs never win the pivot search: i?amax), denormal and
+    huge pivots outside the fast reciprocal's range — with padded strides, an odd batch, and all three entry points."""
+    lib.jb_init(-1)
+    n, batch = 32, 333
+    A = batch_rand(rng, "d", batch, n); b = batch_rand(rng, "d", batch, n, 1)
+    A[3:40] = rng.integers(-2, 3, A[3:40].shape)
+    A[41, 5, :] = 0.0                         # column 5 of system 41 is zero: info = 6
+    A[42, 7, 11] = np.nan                     # a NaN inside column 7
+    A[43, :, 3] = np.nan                      # a NaN row
+    A[44, 9, 20] = np.inf
+    A[45] *= 1e-300; A[46] *= 1e300           # pivots outside [2^-959, 2^957]
+    A[47, 0, :] = [2.0 ** -1074] + [0.0] * 31
+    sa, sb = n * n + 64, n + 8                # padded strides between systems
+    Abuf = np.full((batch, sa), np.nan); Abuf[:, :n * n] = A.reshape(batch, -1)
+    bbuf = np.full((batch, sb), np.nan); bbuf[:, :n] = b.reshape(batch, -1)
+    # reference: the oracle's unscreened ?getf2 + ?getrs (the batched entry points have no LAPACKE NaN screen)
+    getf2, getrs = orc.lib.oracle_dgetf2, orc.lib.oracle_dgetrs_cm
+    getf2.restype = C.c_int; getf2.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    getrs.restype = None; getrs.argtypes = [C.c_char, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    LUo, Xo = A.copy(), b.copy()
+    pivo = np.zeros((batch, n), np.int32); infoo = np.zeros(batch, np.int32)
+    for i in range(batch):
+        infoo[i] = getf2(n, n, LUo[i].ctypes.data, n, pivo[i].ctypes.data)
+        if infoo[i] == 0:
+            getrs(b"N", n, 1, LUo[i].ctypes.data, n, pivo[i].ctypes.data, Xo[i].ctypes.data, n)
+    ok = infoo == 0
+    assert infoo[41] == 6 and ok.sum() >= batch - 3
+    lib.jb_set_option(b"lu32.variant", variant)
+    try:
+        dA, dB = Dev(Abuf.copy()), Dev(bbuf.copy())
+        dP, dI = Dev(np.zeros((batch, n), np.int32)), Dev(np.full(batch, -7, np.int32))
+        check(lib.jb_dgesv_batched(n, 1, dA.ptr, n, sa, dP.ptr, dB.ptr, n, sb, dI.ptr, batch), "gesv_batched"); check(lib.jb_sync(), "sync")
+        LU, X = dA.get(), dB.get()
+        np.testing.assert_array_equal(dI.get(), infoo)
+        np.testing.assert_array_equal(dP.get(), pivo)
+        assert_same_bits(LU[:, :n * n], LUo.reshape(batch, -1))
+        assert_same_bits(X[ok, :n], Xo[ok].reshape(-1, n))
+        assert_same_bits(X[~ok, :n], b[~ok].reshape(-1, n))
+        assert np.isnan(LU[:, n * n:]).all() and np.isnan(X[:, n:]).all()                                      # padding untouched
+        # getrf only, and the solve-only contract (inputs untouched)
+        dA2, dP2, dI2 = Dev(Abuf.copy()), Dev(np.zeros((batch, n), np.int32)), Dev(np.full(batch, -7, np.int32))
+        check(lib.jb_dgetrf_batched(n, dA2.ptr, n, sa, dP2.ptr, dI2.ptr, batch), "getrf_batched"); check(lib.jb_sync(), "sync")
+        assert_same_bits(dA2.get()[:, :n * n], LUo.reshape(batch, -1))
+        np.testing.assert_array_equal(dP2.get(), pivo); np.testing.assert_array_equal(dI2.get(), infoo)
+        dA3, dB3, dX3, dI3 = Dev(Abuf.copy()), Dev(bbuf.copy()), Dev(np.zeros((batch, sb))), Dev(np.zeros(batch, np.int32))
+        check(lib.jb_dsolve_batched(n, 1, dA3.ptr, n, sa, dB3.ptr, n, sb, dX3.ptr, n, sb, dI3.ptr, batch), "dsolve_batched"); check(lib.jb_sync(), "sync")
+        assert_same_bits(dX3.get()[ok, :n], Xo[ok].reshape(-1, n))
+        np.testing.assert_array_equal(dA3.get().view(np.int64), Abuf.view(np.int64))
+        np.testing.assert_array_equal(dI3.get(), infoo)
+    finally:
+        lib.jb_set_option(b"lu32.variant", -1)
 
 
 def test_config3_full_size_properties():
