@@ -67,7 +67,35 @@ for _pfx in ("", "jb_"):
     _sig(_pfx + "cblas_dtrsm", None, _i, _i, _i, _i, _i, _i, _i, _d, _p, _i, _p, _i)
     _sig(_pfx + "cblas_ctrsm", None, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _i)
     _sig(_pfx + "cblas_ztrsm", None, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _i)
+    _sz = C.c_size_t
+    for _t, _ct in (("s", _f), ("d", _d)):
+        _sig(f"{_pfx}cblas_{_t}trmm", None, _i, _i, _i, _i, _i, _i, _i, _ct, _p, _i, _p, _i)
+        _sig(f"{_pfx}cblas_{_t}symm", None, _i, _i, _i, _i, _i, _ct, _p, _i, _p, _i, _ct, _p, _i)
+        _sig(f"{_pfx}cblas_{_t}copy", None, _i, _p, _i, _p, _i)
+        _sig(f"{_pfx}cblas_{_t}swap", None, _i, _p, _i, _p, _i)
+        _sig(f"{_pfx}cblas_{_t}scal", None, _i, _ct, _p, _i)
+        _sig(f"{_pfx}cblas_{_t}axpy", None, _i, _ct, _p, _i, _p, _i)
+        _sig(f"{_pfx}cblas_{_t}dot", _ct, _i, _p, _i, _p, _i)
+        _sig(f"{_pfx}cblas_{_t}nrm2", _ct, _i, _p, _i)
+        _sig(f"{_pfx}cblas_{_t}asum", _ct, _i, _p, _i)
+        _sig(f"{_pfx}cblas_i{_t}amax", _sz, _i, _p, _i)
+    _sig(f"{_pfx}cblas_dsdot", _d, _i, _p, _i, _p, _i)
+    for _t, _ct, _rt in (("c", _f, "s"), ("z", _d, "d")):
+        _sig(f"{_pfx}cblas_{_t}trmm", None, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _i)
+        _sig(f"{_pfx}cblas_{_t}symm", None, _i, _i, _i, _i, _i, _p, _p, _i, _p, _i, _p, _p, _i)
+        _sig(f"{_pfx}cblas_{_t}hemm", None, _i, _i, _i, _i, _i, _p, _p, _i, _p, _i, _p, _p, _i)
+        _sig(f"{_pfx}cblas_{_t}copy", None, _i, _p, _i, _p, _i)
+        _sig(f"{_pfx}cblas_{_t}swap", None, _i, _p, _i, _p, _i)
+        _sig(f"{_pfx}cblas_{_t}scal", None, _i, _p, _p, _i)
+        _sig(f"{_pfx}cblas_{_t}{_rt}scal", None, _i, _ct, _p, _i)
+        _sig(f"{_pfx}cblas_{_t}axpy", None, _i, _p, _p, _i, _p, _i)
+        _sig(f"{_pfx}cblas_{_t}dotu_sub", None, _i, _p, _i, _p, _i, _p)
+        _sig(f"{_pfx}cblas_{_t}dotc_sub", None, _i, _p, _i, _p, _i, _p)
+        _sig(f"{_pfx}cblas_{_rt}{_t}nrm2", _ct, _i, _p, _i)
+        _sig(f"{_pfx}cblas_{_rt}{_t}asum", _ct, _i, _p, _i)
+        _sig(f"{_pfx}cblas_i{_t}amax", _sz, _i, _p, _i)
     for _t in "sdcz":
+        _sig(f"{_pfx}LAPACKE_{_t}potri", _i, _i, _c, _i, _p, _i)
         _sig(f"{_pfx}LAPACKE_{_t}gesv", _i, _i, _i, _i, _p, _i, _p, _p, _i)
         _sig(f"{_pfx}LAPACKE_{_t}getrf", _i, _i, _i, _i, _p, _i, _p)
         _sig(f"{_pfx}LAPACKE_{_t}getrs", _i, _i, _c, _i, _i, _p, _i, _p, _p, _i)
@@ -83,6 +111,13 @@ for _t in "sdcz":
     _sig(f"jb_{_t}potrf_batched", _i, _c, _i, _p, _i, _ll, _p, _i)
     _sig(f"jb_{_t}potrs_batched", _i, _c, _i, _i, _p, _i, _ll, _p, _i, _ll, _i)
     _sig(f"jb_{_t}lacpy", _i, _i, _i, _i, _p, _i, _p, _i)
+_sig("jb_slaset", _i, _i, _i, _f, _f, _p, _i)
+_sig("jb_dlaset", _i, _i, _i, _d, _d, _p, _i)
+_sig("jb_claset", _i, _i, _i, _p, _p, _p, _i)
+_sig("jb_zlaset", _i, _i, _i, _p, _p, _p, _i)
+for _t in "sdcz":
+    _sig(f"jb_{_t}set_diag", _i, _i, _i, _i, _p, _i, _p, _i)
+    _sig(f"jb_{_t}mult_diag", _i, _i, _i, _i, _p, _i, _p, _p, _i)
 _sig("jb_dsolve_batched", _i, _i, _i, _p, _i, _ll, _p, _i, _ll, _p, _i, _ll, _p, _i)
 _sig("jb_dfill_uniform", _i, _p, _i, _i, _i, _ll, _ll, C.c_uint64, _i, _d)
 _sig("jb_sfill_uniform", _i, _p, _i, _i, _i, _ll, _ll, C.c_uint64, _i, _f)

@@ -1585,6 +1585,11 @@ template <typename T>
 int trsm_device(int side, int uplo, int trans, int diag, int m, int n, T alpha, const T *A, int lda, T *B, int ldb,
                 cudaStream_t s) {
   if (m <= 0 || n <= 0) return 0;
+  if (Num<T>::re(alpha) == 0 && Num<T>::im(alpha) == 0) {
+    // ?trsm: alpha == 0 sets B := 0 without referencing A (NaN / Inf in B or a zero diagonal must not leak through)
+    for (int j = 0; j < n; j++) JB_CUDA(cudaMemsetAsync(B + (size_t)j * ldb, 0, sizeof(T) * (size_t)m, s));
+    return 0;
+  }
   if (!(Num<T>::re(alpha) == 1 && Num<T>::im(alpha) == 0)) {
     dim3 grid((unsigned)min((m + 255) / 256, 1024), (unsigned)min(n, 4096));
     scale_kernel<T><<<grid, 256, 0, s>>>(m, n, alpha, B, ldb);

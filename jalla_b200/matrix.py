@@ -165,8 +165,78 @@ def matrixCopy(a: Matrix, trans: int = NoTrans) -> Matrix:
     return ret
 
 
+def referenceMatrixCopy(a: Matrix, trans: int = NoTrans) -> Matrix:
+    """matrixCopy exactly as the unmodified reference performs it on a CMatrix (Matrix.hs:855-878): one strided
+    cblas_?copy per row of the destination (rowsRef / columnsRef vectors, CVector.hs:284-288) — here on device pointers,
+    which libjalla_b200's level-1 entry points accept.  r kernel launches; matrixCopy above is the one-launch form."""
+    r, c = a.shape
+    ret = matrixAlloc(_shape_trans(trans, a.shape), a.t)
+    copy = getattr(lib, f"cblas_{a.t}copy")
+    es = a.itemsize
+    if trans == NoTrans:
+        for i in range(r):      # row i of A (stride lda) -> row i of the copy
+            copy(c, a.ptr + es * i, a.lda, ret.ptr + es * i, ret.lda)
+    else:
+        for j in range(c):      # column j of A (stride 1) -> row j of the copy
+            copy(r, a.ptr + es * a.lda * j, 1, ret.ptr + es * j, ret.lda)
+    check_last("matrixCopy")
+    return ret
+
+
+def _scalar_ptrs(t: str, *vals):
+    arr = np.array(vals, dtype=_NP[t])
+    return [C.c_void_p(arr.ctypes.data + i * arr.itemsize) for i in range(len(vals))], arr
+
+
+def fillMatrix(shape, value, dtype="d") -> Matrix:
+    """createMatrix shape (fill value) on the device (Matrix.hs:798-819,1050-1060 do it with per-element pokes)."""
+    t = _letter(dtype)
+    m = matrixAlloc(shape, t)
+    if t in "sd":
+        check(getattr(lib, f"jb_{t}laset")(shape[0], shape[1], value, value, m.ptr, m.lda), "fill")
+    else:
+        (p,), keep = _scalar_ptrs(t, value)
+        check(getattr(lib, f"jb_{t}laset")(shape[0], shape[1], p, p, m.ptr, m.lda), "fill")
+    return m
+
+
 def idMatrix(n: int, dtype="d") -> Matrix:
-    return Matrix.from_numpy(np.eye(n, dtype=_NP[_letter(dtype)], order="F"))
+    """idMatrix n = createMatrix (n,n) $ fill 0 >> setDiag 0 (repeat 1)  (Matrix.hs:525-526), one device kernel."""
+    t = _letter(dtype)
+    m = matrixAlloc((n, n), t)
+    if t in "sd":
+        check(getattr(lib, f"jb_{t}laset")(n, n, 0.0, 1.0, m.ptr, m.lda), "idMatrix")
+    else:
+        (p0, p1), keep = _scalar_ptrs(t, 0, 1)
+        check(getattr(lib, f"jb_{t}laset")(n, n, p0, p1, m.ptr, m.lda), "idMatrix")
+    return m
+
+
+def setDiag(m: Matrix, d: int, values) -> None:
+    """setDiag d values (Matrix.hs:1023-1036): only as many values as fit in the diagonal are used."""
+    v = np.ascontiguousarray(values, dtype=m.dtype)
+    check(getattr(lib, f"jb_{m.t}set_diag")(m.shape[0], m.shape[1], d, v.ctypes.data, v.size, m.ptr, m.lda), "setDiag")
+
+
+def matrixMultDiag(at: Tuple[Matrix, int], d) -> Matrix:
+    """matrixMultDiag (a,t) d = op(A) * diag(d)  (Matrix.hs:660-665: modifyMatrix a t $ zipWithM_ scaleColumn d [0..c-1]),
+    one fused transpose-copy-and-scale kernel instead of a copy plus c cblas_?scal calls."""
+    a, t = at
+    r, c = _shape_trans(t, a.shape)
+    v = np.ascontiguousarray(list(d)[:c] if not isinstance(d, np.ndarray) else d[:c], dtype=a.dtype)
+    if v.size < c:      # zipWithM_ stops at the shorter list: the remaining columns are copied unscaled
+        v = np.concatenate([v, np.ones(c - v.size, dtype=a.dtype)])
+    out = matrixAlloc((r, c), a.t)
+    check(getattr(lib, f"jb_{a.t}mult_diag")(t, r, c, a.ptr, a.lda, v.ctypes.data, out.ptr, out.lda), "matrixMultDiag")
+    return out
+
+
+def pseudoInverseFromSVD(u: Matrix, s, vt: Matrix) -> Matrix:
+    """The GEMM tail of pseudoInverse (Matrix.hs:544-551): (matrixMultDiag (vt,Trans) s', NoTrans) ##! (u,Trans) with
+    s' = 1/s where s /= 0.  The SVD itself (gesvd) is outside the hot path; u, s, vt come from the caller."""
+    s = np.asarray(s, dtype=np.float64)
+    sinv = np.where(s != 0, 1.0 / np.where(s != 0, s, 1.0), 0.0)
+    return mmT((matrixMultDiag((vt, Trans), sinv.astype(vt.dtype)), NoTrans), (u, Trans))
 
 
 def unsafeSolveLinearSystem(a: Matrix, b: Matrix) -> None:

@@ -108,3 +108,42 @@ def test_managed_memory_is_host_dereferenceable(J, rng):
     finally:
         for p in bufs:
             lib.jb_free(p)
+
+
+@pytest.mark.parametrize("t", "sdcz")
+def test_device_construction_helpers(J, rng, t):
+    """idMatrix / fill / setDiag / matrixMultDiag on the device (Matrix.hs:525-526,660-665,1023-1036) and the reference's
+    own row-by-row matrixCopy (Matrix.hs:855-878) running on device pointers through cblas_?copy."""
+    n = 45
+    np.testing.assert_array_equal(J.idMatrix(n, t).to_numpy(), np.eye(n, dtype=NP[t]))
+    f = J.fillMatrix((7, 11), 2.5, t)
+    np.testing.assert_array_equal(f.to_numpy(), np.full((7, 11), 2.5, dtype=NP[t]))
+    J.setDiag(f, 2, [1, 2, 3] + [9] * 20)                      # more values than fit: the surplus is ignored
+    ref = np.full((7, 11), 2.5, dtype=NP[t]); ref[np.arange(7), np.arange(7) + 2] = ([1, 2, 3] + [9] * 4)
+    np.testing.assert_array_equal(f.to_numpy(), ref)
+    a = jalla_arbitrary(rng, t, 33, 58)
+    A = J.Matrix.from_numpy(a)
+    for tr in (J.NoTrans, J.Trans):
+        src = a if tr == J.NoTrans else a.T
+        np.testing.assert_array_equal(J.referenceMatrixCopy(A, tr).to_numpy(), src)
+        np.testing.assert_array_equal(J.matrixCopy(A, tr).to_numpy(), src)
+        d = rng.uniform(-2, 2, src.shape[1]).astype(NP[t])
+        got = J.matrixMultDiag((A, tr), d).to_numpy()
+        # tests/Test.hs:77-103: multiplying by a diagonal matrix through GEMM equals the column scaling exactly
+        D = J.Matrix.from_numpy(np.asfortranarray(np.diag(d)))
+        via_gemm = J.mmT((A, tr), (D, J.NoTrans)).to_numpy()
+        np.testing.assert_array_equal(got, (src * d[None, :]).astype(NP[t]))
+        assert fro(got - via_gemm) <= 4 * EPS[t] * fro(got)
+
+
+def test_prop_pseudoInverse_on_device(J, rng):
+    """tests/Test.hs:106-112 with the whole tail of pseudoInverse (Matrix.hs:544-551) on the device:
+    matrixMultDiag (vt,Trans) s' then ##! with (u,Trans); only the SVD (gesvd, out of scope) is numpy's."""
+    for _ in range(5):
+        mat = jalla_arbitrary(rng, "d")
+        m, n = mat.shape
+        u, s, vt = np.linalg.svd(mat, full_matrices=False)
+        P = J.pseudoInverseFromSVD(J.Matrix.from_numpy(np.asfortranarray(u)), s, J.Matrix.from_numpy(np.asfortranarray(vt)))
+        Mx = J.Matrix.from_numpy(mat)
+        a = np.eye(m) - (Mx @ P).to_numpy() if m < n else np.eye(n) - (P @ Mx).to_numpy()
+        assert np.linalg.norm(a) < 1e-6
