@@ -104,7 +104,7 @@ def run_reference(args):
     ob = cpu_ref.openblas()
     cores = os.cpu_count() or 1
     cpu_ref.openblas_set_threads(cores)
-    n = 8192                                  # bounded sample of the N=16384 workload (1/8 of its flops)
+    n = N_GEMM                                # the configuration itself: one cblas_dgemm N=16384 per step (~9 s on 16 cores)
     from jalla_b200 import synth
     A = synth.uniform(n, n, SEED, "d"); B = synth.uniform(n, n, SEED + 1, "d")
     Cm = np.empty((n, n), order="F")
@@ -119,13 +119,13 @@ def run_reference(args):
     ms = 1e3 * sum(times) / len(times)
     val = flop / (ms * 1e-3) / 1e12
     lu = cpu_batched_lu(ob, sample=200000, threads=cores)
-    sample = f"cblas_dgemm N={n} (1/8 of the N=16384 step's flops) per step, OpenBLAS {ob.info.get('core')} x{cores} threads"
+    sample = f"one cblas_dgemm N={n} (the whole configs[1] product) per step, OpenBLAS {ob.info.get('core')} x{cores} threads"
     line = {
         "impl": "reference", "metric": "dgemm_fp64_n16384_tflops", "value": val, "unit": "TFLOP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "configs[1]: FP64 dgemm N=16384 square (CPU arm runs a bounded N=8192 sample per step)",
-                   "trans": "NN", "alpha": 1, "beta": 0, "layout": "column-major"},
+        "config": {"workload": "configs[1]: FP64 dgemm N=16384 square, C=A*B (NN, alpha=1, beta=0), column-major ld=rows",
+                   "n": n, "inputs": "counter-based U(-1,1) keyed on global (i,j) (numpy twin of the device generator)"},
         "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": cores, "kind": "reference", "sample": sample,
                          "blas": ob.info.get("config")},
         "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -204,6 +204,118 @@ def small_config(torch, lib, check, stream):
     return {"workload": "configs[0]: Double 512x512 multiply + LU solve (gesv nrhs=1), device-resident vs OpenBLAS host",
             "gpu_dgemm_ms": t_gemm, "gpu_dgesv_ms": t_gesv, "cpu_dgemm_ms": c_gemm, "cpu_dgesv_ms": c_gesv,
             "gpu_dgemm_tflops": 2.0 * n ** 3 / (t_gemm * 1e-3) / 1e12}
+
+
+
+def verify_columns(np, torch, gemm, ncols):
+    """Column-sampled full check of the distributed product: `ncols` random columns of this rank's C block, every row,
+    against numpy's dgemm on the host (A row block and the sampled B columns copied back from the device; the panels a
+    rank pulled from its peers are themselves compared with the regenerated inputs on sampled rows / columns).
+    Returns (relative Frobenius error, north_star bound 4*n*eps*|A||B|/|C|)."""
+    from jalla_b200 import synth
+    P, n, t = gemm.plan, gemm.n, gemm.t
+    mb, nb = P["mb"], P["nb"]
+    dt = {"s": np.float32, "d": np.float64, "c": np.complex64, "z": np.complex128}[t]
+    rng = np.random.default_rng(1000 + gemm.grid.rank)
+    cols = np.sort(rng.choice(nb, size=min(ncols, nb), replace=False))
+    A = np.empty((mb, n), dtype=dt, order="F")
+    gemm.check(gemm.lib.jb_memcpy_d2h(A.ctypes.data, gemm.A_ptr, A.nbytes), "verify d2h A")
+    Bs = np.empty((n, len(cols)), dtype=dt, order="F")
+    Cs = np.empty((mb, len(cols)), dtype=dt, order="F")
+    es = A.itemsize
+    col = np.empty(n, dtype=dt)
+    for q, j in enumerate(cols):
+        for p in P["panels"]:      # B panel t is a (w x nb) block with ld = w
+            gemm.check(gemm.lib.jb_memcpy_d2h(col.ctypes.data + p["k0"] * es, gemm.b_ptrs[p["t"]] + int(j) * p["w"] * es, p["w"] * es), "verify d2h B")
+        Bs[:, q] = col
+        gemm.check(gemm.lib.jb_memcpy_d2h(Cs[:, q].ctypes.data, gemm.C.data_ptr() + int(j) * mb * es, mb * es), "verify d2h C")
+    # the operands on the device are the generator's (covers the peer pulls): sampled rows of A, all sampled columns of B
+    for i in rng.choice(mb, size=4, replace=False):
+        np.testing.assert_array_equal(A[i], synth.uniform(1, n, gemm.seed, t, P["row0"] + int(i), 0)[0])
+    for q, j in enumerate(cols[:8]):
+        np.testing.assert_array_equal(Bs[:, q], synth.uniform(n, 1, gemm.seed + 1, t, 0, P["col0"] + int(j))[:, 0])
+    ref = A.astype(np.complex128 if t in "cz" else np.float64) @ Bs.astype(np.complex128 if t in "cz" else np.float64)
+    err = float(np.linalg.norm(Cs - ref) / np.linalg.norm(ref))
+    eps = float(np.finfo(np.float32 if t in "sc" else np.float64).eps)
+    bound = 4 * n * eps * float(np.linalg.norm(A)) * float(np.linalg.norm(Bs)) / float(np.linalg.norm(ref))
+    return err, bound
+
+
+def factorisations(torch, lib, check, stream):
+    """Large single-GPU LAPACKE calls on device-resident Double data (CUDA events around the call, copies subtracted):
+    dgetrf / dpotrf / dgesv (nrhs = 1, the Jalla call) at 8192 and 16384, as fractions of the measured DMMA peak."""
+    out = {}
+    for n in (8192, 16384):
+        A0 = torch.empty(n * n, dtype=torch.float64, device="cuda"); A = torch.empty_like(A0)
+        b0 = torch.empty(n, dtype=torch.float64, device="cuda"); b = torch.empty_like(b0)
+        piv = torch.empty(n, dtype=torch.int32, device="cuda")
+
+        def ev(fn, reps=2):
+            fn(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(reps):
+                fn()
+            e1.record(stream); torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
+        t_copy = ev(lambda: A.copy_(A0))
+        check(lib.jb_dfill_uniform(A0.data_ptr(), n, n, n, 0, 0, SEED, 0, 0.0), "fill")
+        check(lib.jb_dfill_uniform(b0.data_ptr(), n, n, 1, 0, 0, SEED + 2, 0, 0.0), "fill")
+
+        def getrf():
+            A.copy_(A0); assert lib.LAPACKE_dgetrf(102, n, n, A.data_ptr(), n, piv.data_ptr()) == 0
+
+        def gesv():
+            A.copy_(A0); b.copy_(b0); assert lib.LAPACKE_dgesv(102, n, 1, A.data_ptr(), n, piv.data_ptr(), b.data_ptr(), n) == 0
+        t_getrf, t_gesv = ev(getrf) - t_copy, ev(gesv) - t_copy
+        check(lib.jb_dfill_uniform(A0.data_ptr(), n, n, n, 0, 0, SEED + 3, 1, float(n)), "fill spd")
+
+        def potrf():
+            A.copy_(A0); assert lib.LAPACKE_dpotrf(102, b"L", n, A.data_ptr(), n) == 0
+        t_potrf = ev(potrf) - t_copy
+        f_lu, f_ch = 2.0 / 3.0 * n ** 3, n ** 3 / 3.0
+        out[f"n{n}"] = {"dgetrf_ms": t_getrf, "dgetrf_tflops": f_lu / t_getrf / 1e9, "dgetrf_frac_of_dmma_peak": f_lu / t_getrf / 1e9 / DMMA_PEAK_TFLOPS,
+                        "dgesv_nrhs1_ms": t_gesv, "dpotrf_ms": t_potrf, "dpotrf_tflops": f_ch / t_potrf / 1e9,
+                        "dpotrf_frac_of_dmma_peak": f_ch / t_potrf / 1e9 / DMMA_PEAK_TFLOPS}
+        del A0, A, b0, b, piv
+        torch.cuda.empty_cache()
+    return out
+
+
+def cholesky_config3(torch, lib, grid, dist, n=65536, nb=1024):
+    """BASELINE.json configs[3]: dpotrf + dpotrs (nrhs = 1) of an N x N SPD Double matrix, 2-D block-cyclic over the
+    ranks with NCCL panel broadcasts (jalla_b200/dist_chol.py); one warm-up pass, one timed pass, residual of the solve."""
+    from jalla_b200.dist_chol import DistCholesky, DeviceOps
+    ops = DeviceOps()
+    ch = DistCholesky(grid, n, nb, ops)
+    best = None
+    for rep in range(2):
+        ch.fill_spd(); ch.info = 0
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        info = ch.potrf(lookahead=True)
+        e1.record()
+        b = ops.empty(n); ops.fill_uniform(b, 0, n, n, 1, 0, 0, 777)
+        x = b.clone()
+        ch.potrs(x, 1)
+        e2.record(); torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t = torch.tensor([e0.elapsed_time(e1), e1.elapsed_time(e2)], device="cuda", dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        best = (t[0].item(), t[1].item())
+    res = ch.residual(x, b, 1)
+    ops.finish()
+    flop = n ** 3 / 3.0
+    world = grid.world
+    return {"workload": "configs[3]: dpotrf + dpotrs (nrhs=1), N=65536 SPD Double, 2-D block-cyclic over the ranks, NCCL panel broadcast",
+            "n": n, "tile": nb, "grid": f"{grid.pr}x{grid.pc}", "n_gpus": world, "info": int(info), "potrf_ms": best[0], "potrs_ms": best[1],
+            "tflops": flop / (best[0] * 1e-3) / 1e12, "frac_of_dmma_peak": flop / (best[0] * 1e-3) / 1e12 / (DMMA_PEAK_TFLOPS * world),
+            "solve_residual_over_n_eps": float(res)}
 
 
 # ------------------------------------------------------------------------------ GPU arm
@@ -291,7 +403,15 @@ def main():
             dist.all_reduce(tms, op=dist.ReduceOp.MAX)
             ms = float(tms.item())
         res["gemm"] = (ms, gemm_launches, kern_ms, t_wall0, t_wall1)
-        gemm.verify_sample()
+        err, bound = verify_columns(np, torch, gemm, max(64 // world, 8))
+        v = torch.tensor([err, err / bound], device="cuda", dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        res["verify"] = {"what": f"{max(64 // world, 8)} random columns x all rows of every rank's C block vs numpy dgemm on the host; "
+                                 "pulled operands vs the regenerated inputs", "columns_total": max(64 // world, 8) * world,
+                         "rel_frobenius_err_max": float(v[0].item()), "err_over_bound_max": float(v[1].item()),
+                         "bound": "4*n*eps*|A||B|/|C| (north_star)", "ok": bool(v[1].item() <= 1.0)}
+        assert res["verify"]["ok"], res["verify"]
     # ---------------------------------------------------------------- secondary: batched LU
     lu = None
     if args.only in ("", "lu"):
@@ -335,6 +455,7 @@ def main():
                          "algorithmic_flops_per_launch": local_flop},
             "gpu_launches": int(total_launches),
             "clocks": sampler.summary(tw0, tw1),
+            "verify": res["verify"],
         })
     if "lu" in res:
         lu_ms, lu_kern_ms = res["lu"]
@@ -346,8 +467,9 @@ def main():
             "config": {"workload": "configs[2]: 1,000,000 independent 32x32 Double systems, getrf+getrs (jb_dgesv_batched), "
                                    "batch split across ranks, no collective", "flush": "8.4 GB working set >> L2"},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                         # dram__bytes_read+write of one 10^6-system launch (profiles/ncu_lu32_r1b.txt) = algorithmic bytes
-                         "traffic": 16.98e9 if world == 1 else None, "peak_source": hbm_src, "kernel": "lu32v2_kernel<1,1,16>",
+                         # dram__bytes_read + dram__bytes_write of the shipped kernel: 4.988 GB per 296,000 systems
+                         # (profiles/ncu_lu32q_r2.txt) scaled to this launch = the algorithmic bytes
+                         "traffic": per_rank * 16850.0, "peak_source": hbm_src, "kernel": "lu32q_kernel<1,1,16> (pair-lookahead)",
                          "kernel_ms": lu_kern_ms, "algorithmic_bytes_per_launch": per_rank * LU_BYTES_PER_SYSTEM,
                          "frac_of_nominal_8TBs": ach / 8000.0},
         }
@@ -379,10 +501,12 @@ def main():
                 tms = torch.tensor([ms_o], device="cuda", dtype=torch.float64)
                 dist.all_reduce(tms, op=dist.ReduceOp.MAX)
                 ms_o = float(tms.item())
-            g2.verify_sample(samples=3)
+            err_o, bound_o = verify_columns(np, torch, g2, 8)
+            assert err_o <= bound_o, (t, err_o, bound_o)
             tf = g2.flop / (ms_o * 1e-3) / 1e12
             other[f"{t}gemm_n{n}"] = {"tflops": tf, "ms": ms_o, "flop": g2.flop, "peak_tflops": peak * world, "frac": tf / (peak * world),
-                                      "pipe": bound, "n_gpus": world}
+                                      "pipe": bound, "n_gpus": world, "verify_rel_frobenius_err": err_o, "verify_bound": bound_o}
+            g2.close()
             del g2
             torch.cuda.empty_cache()
         out["other_configs"] = other
@@ -392,6 +516,32 @@ def main():
     # ---------------------------------------------------------------- e2e through the C ABI with host buffers
     if "gemm" in res and not args.no_e2e:
         out["e2e"] = gemm.e2e(steps=min(args.steps, 2))
+        if world == 1:
+            # the link-level drop-in hands over what stock Jalla allocates: pageable memory (mallocForeignPtrArray)
+            n = N_GEMM
+            Ah = np.empty((n, n), order="F"); Bh = np.empty((n, n), order="F"); Ch = np.empty((n, n), order="F")
+            check(lib.jb_memcpy_d2h(Ah.ctypes.data, gemm.A_ptr, Ah.nbytes), "d2h"); check(lib.jb_memcpy_d2h(Bh.ctypes.data, gemm.B_ptr, Bh.nbytes), "d2h")
+            t0 = time.perf_counter()
+            lib.cblas_dgemm(102, 111, 111, n, n, n, 1.0, Ah.ctypes.data, n, Bh.ctypes.data, n, 0.0, Ch.ctypes.data, n)
+            dt = time.perf_counter() - t0
+            check_last("pageable e2e")
+            out["e2e"]["pageable_host"] = {"value": 2.0 * n ** 3 / dt / 1e12, "unit": "TFLOP/s", "ms_per_step": dt * 1e3,
+                                           "path": "cblas_dgemm(pageable numpy A,B,C), one call"}
+            del Ah, Bh, Ch
+    if "lu" in res and not args.no_e2e and "batched_lu" in out:
+        lu2 = jdist.ShardedBatchedLU(grid, LU_N, LU_BATCH, seed=SEED)
+        out["batched_lu"]["e2e"] = lu2.e2e(steps=2)
+        del lu2
+        torch.cuda.empty_cache()
+    if world == 1 and args.only == "" and not args.no_other:
+        out["factorisations"] = factorisations(torch, lib, check, stream)
+    if world == 8 and args.only == "" and not args.no_other:
+        gemm.close()
+        del gemm
+        torch.cuda.empty_cache()
+        ch = cholesky_config3(torch, lib, grid, dist)
+        if rank == 0:
+            out["dpotrf_n65536"] = ch
     # ---------------------------------------------------------------- CPU baseline (rank 0, N=1 only)
     if world == 1 and not args.no_cpu and "gemm" in res:
         from oracle import cpu_ref
@@ -413,6 +563,10 @@ def main():
     if rank == 0:
         print(json.dumps(out), flush=True)
     if dist is not None:
+        try:
+            gemm.close()
+        except NameError:
+            pass
         dist.destroy_process_group()
     return 0
 

@@ -46,6 +46,10 @@ _sig("jb_free", None, _p)
 _sig("jb_memcpy_h2d", _i, _p, _p, C.c_size_t)
 _sig("jb_memcpy_d2h", _i, _p, _p, C.c_size_t)
 _sig("jb_memcpy_d2d", _i, _p, _p, C.c_size_t)
+_sig("jb_memcpy_async", _i, _p, _p, C.c_size_t, _p)
+_sig("jb_ipc_export", _i, _p, _p)
+_sig("jb_ipc_open", _p, _p)
+_sig("jb_ipc_close", _i, _p)
 _sig("jb_sync", _i)
 _sig("jb_set_stream", None, _p)
 _sig("jb_get_stream", _p)

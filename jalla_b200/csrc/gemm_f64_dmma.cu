@@ -226,11 +226,7 @@ static int make_map(CUtensorMap *map, const double *ptr, long rows, long cols, i
 template <bool A_KM, bool B_KM>
 static int launch(const CUtensorMap &ma, const CUtensorMap &mb, int m, int n, int k, double alpha, double beta, double *C,
                   int ldc, int tri, cudaStream_t s) {
-  static bool attr = false;
-  if (!attr) {
-    JB_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<A_KM, B_KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr = true;
-  }
+  JB_ONCE_PER_DEVICE(JB_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<A_KM, B_KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)));
   const int ntiles = ((m + BM - 1) / BM) * ((n + BN - 1) / BN);
   int grid = ntiles < num_sms() ? ntiles : num_sms();
   // "gemm.max_ctas": a CTA of this persistent kernel owns a whole SM (registers + shared memory), so callers that

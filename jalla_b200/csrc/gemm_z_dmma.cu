@@ -213,11 +213,7 @@ zgemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 template <bool A_KM, bool B_KM>
 static int launch(const CUtensorMap &ma, const CUtensorMap &mb, int m, int n, int k, cdouble alpha, cdouble beta,
                   cdouble *C, int ldc, int tri, int ca, int cb, cudaStream_t s) {
-  static bool attr = false;
-  if (!attr) {
-    JB_CUDA(cudaFuncSetAttribute(zgemm_dmma_kernel<A_KM, B_KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr = true;
-  }
+  JB_ONCE_PER_DEVICE(JB_CUDA(cudaFuncSetAttribute(zgemm_dmma_kernel<A_KM, B_KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)));
   const int ntiles = ((m + BM - 1) / BM) * ((n + BN - 1) / BN);
   int grid = ntiles < num_sms() ? ntiles : num_sms();
   // "gemm.max_ctas": a CTA of this persistent kernel owns a whole SM (registers + shared memory), so callers that

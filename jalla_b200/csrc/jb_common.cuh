@@ -133,7 +133,17 @@ ThreadState &tls();
 void set_error(int code, const char *fmt, ...);
 extern std::atomic<uint64_t> g_launches;
 inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
-int option(const char *key);   // -1 when unset
+int option(const char *key);   // -1 when unset; `key` must be a string literal (values are cached per thread by pointer)
+
+// Runs `stmt` the first time a call site is reached on each device (cudaFuncSetAttribute is per device / context).
+#define JB_ONCE_PER_DEVICE(stmt)                                                                   \
+  do {                                                                                             \
+    static std::atomic<uint64_t> done__{0};                                                        \
+    int dev__ = 0;                                                                                 \
+    cudaGetDevice(&dev__);                                                                         \
+    const uint64_t bit__ = 1ull << (dev__ & 63);                                                   \
+    if (!(done__.load(std::memory_order_acquire) & bit__)) { stmt; done__.fetch_or(bit__, std::memory_order_release); } \
+  } while (0)
 
 #define JB_CUDA(call)                                                                         \
   do {                                                                                        \

@@ -29,10 +29,23 @@ void set_error(int code, const char *fmt, ...) {
   va_end(ap);
 }
 
+static std::atomic<unsigned> g_opt_version{0};
+// Hot paths ask for options on every kernel launch (hundreds per blocked factorisation): the mutex + string-map lookup
+// happens once per thread and key until jb_set_option changes something.
 int option(const char *key) {
-  std::lock_guard<std::mutex> lk(g_mu);
-  auto it = g_options.find(key);
-  return it == g_options.end() ? -1 : it->second;
+  struct Slot { const char *key; unsigned ver; int val; };
+  static thread_local Slot cache[32];
+  const unsigned ver = g_opt_version.load(std::memory_order_acquire) + 1;     // 0 = empty slot
+  Slot &sl = cache[((uintptr_t)key >> 3) & 31];
+  if (sl.key == key && sl.ver == ver) return sl.val;
+  int v;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_options.find(key);
+    v = it == g_options.end() ? -1 : it->second;
+  }
+  sl.key = key; sl.ver = ver; sl.val = v;
+  return v;
 }
 
 int ensure_device() {
@@ -204,6 +217,36 @@ int jb_sync(void) {
   JB_CUDA(cudaStreamSynchronize(tls().stream));
   return 0;
 }
+// ---- peer memory between the one-process-per-GPU ranks of a node ------------------------------------
+// A rank exports a jb_malloc'd device buffer as a 64-byte CUDA IPC handle, its peers map it and pull panels from it with
+// copy-engine transfers over NVLink (jb_memcpy_async on a side stream) — no collective kernel competes with the
+// persistent GEMM for SMs.
+int jb_ipc_export(const void *dev_ptr, void *handle64) {
+  if (int rc = ensure_device()) return rc;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+  JB_CUDA(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)handle64, const_cast<void *>(dev_ptr)));
+  return 0;
+}
+void *jb_ipc_open(const void *handle64) {
+  if (ensure_device()) return nullptr;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  void *p = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) { cudaGetLastError(); set_error(JB_ERR_CUDA, "jb_ipc_open: %s", cudaGetErrorString(e)); return nullptr; }
+  return p;
+}
+int jb_ipc_close(void *p) {
+  if (!p) return 0;
+  JB_CUDA(cudaIpcCloseMemHandle(p));
+  return 0;
+}
+// dst / src: any mix of device, peer-mapped, pinned or pageable memory (UVA); ordered on `cuda_stream`
+int jb_memcpy_async(void *dst, const void *src, size_t bytes, void *cuda_stream) {
+  if (int rc = ensure_device()) return rc;
+  JB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)cuda_stream));
+  return 0;
+}
 void jb_set_stream(void *s) { tls().stream = (cudaStream_t)s; }
 void *jb_get_stream(void) { return (void *)tls().stream; }
 uint64_t jb_kernel_launches(void) { return g_launches.load(); }
@@ -211,6 +254,7 @@ int jb_set_option(const char *key, int value) {
   if (!key) return JB_ERR_ARG;
   std::lock_guard<std::mutex> lk(g_mu);
   g_options[key] = value;
+  g_opt_version.fetch_add(1, std::memory_order_release);
   return 0;
 }
 
