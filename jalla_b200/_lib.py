@@ -115,6 +115,15 @@ for _t in "sdcz":
     _sig(f"jb_{_t}potrf_batched", _i, _c, _i, _p, _i, _ll, _p, _i)
     _sig(f"jb_{_t}potrs_batched", _i, _c, _i, _i, _p, _i, _ll, _p, _i, _ll, _i)
     _sig(f"jb_{_t}lacpy", _i, _i, _i, _i, _p, _i, _p, _i)
+_sig("jb_dist_create", _i, C.POINTER(_p), _i, _i, _i)
+_sig("jb_dist_destroy", _i, _p)
+_sig("jb_dist_ngpus", _i, _p)
+_sig("jb_dist_dgemm", _i, _p, _i, _i, _i, _i, _i, _d, _p, _i, _p, _i, _d, _p, _i)
+_sig("jb_dist_dgetrf", _i, _p, _i, _p, _i, _p)
+_sig("jb_dist_dgetrs", _i, _p, _c, _i, _i, _p, _i, _p, _p, _i)
+_sig("jb_dist_dpotrf", _i, _p, _c, _i, _p, _i)
+_sig("jb_dist_dpotrs", _i, _p, _c, _i, _i, _p, _i, _p, _i)
+_sig("jb_dist_dgesv_batched", _i, _p, _i, _i, _p, _i, _ll, _p, _p, _i, _ll, _p, _i)
 _sig("jb_slaset", _i, _i, _i, _f, _f, _p, _i)
 _sig("jb_dlaset", _i, _i, _i, _d, _d, _p, _i)
 _sig("jb_claset", _i, _i, _i, _p, _p, _p, _i)

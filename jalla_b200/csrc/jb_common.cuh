@@ -127,6 +127,7 @@ struct ThreadState {
   cudaStream_t stream = nullptr;
   int err = 0;
   char msg[256] = {0};
+  int device = -1;          // >= 0: entry points on this thread bind this device instead of the library default (jb_dist_*)
   int gemm_cta_cap = 0;     // > 0: the persistent DMMA GEMMs launched by this thread use at most this many CTAs (SMs)
 };
 ThreadState &tls();
@@ -199,6 +200,7 @@ template <typename T> int nancheck_device(int tri, int m, int n, const T *a, int
 
 // LAPACK-level device routines (column-major, device pointers; ipiv/info device ints)
 template <typename T> int getrf_device(int m, int n, T *A, int lda, int *d_ipiv, int *d_info, cudaStream_t s);
+template <typename T> int laswp_device(T *A, int lda, int ncols, const int *d_ipiv, int k0, int k1, cudaStream_t s);
 template <typename T> int getrs_device(char trans, int n, int nrhs, const T *A, int lda, const int *d_ipiv, T *B, int ldb, cudaStream_t s);
 template <typename T> int getri_device(int n, T *A, int lda, const int *d_ipiv, int *d_info, cudaStream_t s);
 template <typename T> int potrf_device(char uplo, int n, T *A, int lda, int *d_info, cudaStream_t s);

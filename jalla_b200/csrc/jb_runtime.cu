@@ -72,6 +72,7 @@ int ensure_device() {
     dev = cur;
   }
   // `ccall unsafe` can arrive on any OS thread: bind the device per call (H11).
+  if (tls().device >= 0) dev = tls().device;
   int cur = -1;
   if (cudaGetDevice(&cur) != cudaSuccess || cur != dev) JB_CUDA(cudaSetDevice(dev));
   return 0;

@@ -1639,6 +1639,15 @@ int trsm_device(int side, int uplo, int trans, int diag, int m, int n, T alpha, 
   return 0;
 }
 
+// forward row interchanges ipiv[k0..k1) (1-based, global rows = rows of A) on `ncols` columns of A
+template <typename T>
+int laswp_device(T *A, int lda, int ncols, const int *d_ipiv, int k0, int k1, cudaStream_t s) {
+  if (int rc = laswp_launch<T>(A, lda, 0, ncols, d_ipiv, k0, k1, 0, s)) return rc;
+  JB_CUDA(cudaGetLastError());
+  return 0;
+}
+template int laswp_device<double>(double *, int, int, const int *, int, int, cudaStream_t);
+
 #define INST(T)                                                                                        \
   template int getrf_device<T>(int, int, T *, int, int *, int *, cudaStream_t);                        \
   template int getrs_device<T>(char, int, int, const T *, int, const int *, T *, int, cudaStream_t);   \

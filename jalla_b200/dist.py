@@ -58,29 +58,42 @@ class ProcessGrid:
                     self.col_group = g
 
 
-def gemm_plan(n: int, pr: int, pc: int, row: int, col: int, chunks: int = 16):
+def gemm_plan(n: int, pr: int, pc: int, row: int, col: int, chunks: int = 16, owned_first: bool = False):
     """Static description of rank (row,col)'s share of C = A*B (all sizes in elements).
     K is cut into panels that never straddle an owner's K block; panel [k0,k1) of A lives on process column k0//kc
     and of B on process row k0//kr.  Each panel is one broadcast and one local GEMM,
     so only the first panel's transfer is exposed; everything else hides under the DMMA GEMMs."""
     assert n % pr == 0 and n % pc == 0, "N must divide the process grid"
     mb, nb, kr, kc = n // pr, n // pc, n // pr, n // pc
-    # panels may not straddle an ownership boundary (multiples of kr for B, of kc for A).  The first ownership
-    # granule is cut geometrically (g/8, g/8, g/4, g/2) so the exposed first transfer is small; the rest are whole
-    # granules, which keeps the local GEMMs long (few C read-modify-write sweeps, few partial waves).
+    # panels may not straddle an ownership boundary (multiples of kr for B, of kc for A): K is cut into granules of
+    # g = min(kr, kc) columns.  A rank starts with the granules whose operands it already holds (both, then one of
+    # them) while the others are on their way; only the FIRST granule is cut finer — in four equal parts when the rank
+    # owns both operands (the end-to-end path streams them from the host in that order), geometrically
+    # (g/8, g/8, g/4, g/2) when its first product has to wait for a transfer — so that there are few C read-modify-write
+    # sweeps and the exposed first transfer is small.  (The K order differs per rank: C agrees to rounding, not bit for bit.)
     g = min(kr, kc)
     assert kr % g == 0 and kc % g == 0
-    widths = []
-    if chunks > 1 and pr * pc > 1 and g % 8 == 0:
-        widths += [g // 8, g // 8, g // 4, g // 2]
+    granules = []
+    for q in range(n // g):
+        k0 = q * g
+        a_mine, b_mine = k0 // kc == col, k0 // kr == row
+        granules.append((0 if (a_mine and b_mine) else (1 if (a_mine or b_mine) else 2), q))
+    if owned_first and chunks > 1 and pr * pc > 1:
+        granules.sort()              # only for the pull path: collectives need the same panel order on every rank
     else:
-        widths += [g]
-    widths += [g] * (n // g - 1)
-    panels, k0 = [], 0
-    for t, w in enumerate(widths):
-        panels.append({"t": t, "k0": k0, "k1": k0 + w, "w": w, "a_src": row * pc + k0 // kc, "b_src": (k0 // kr) * pc + col,
-                       "a_mine": k0 // kc == col, "b_mine": k0 // kr == row, "beta": 0.0 if t == 0 else 1.0})
-        k0 += w
+        granules = [(1, q) for _, q in granules]
+    panels = []
+    for idx, (cls, q) in enumerate(granules):
+        k0 = q * g
+        if idx == 0 and chunks > 1 and pr * pc > 1 and g % 8 == 0:
+            widths = [g // 4] * 4 if cls == 0 else [g // 8, g // 8, g // 4, g // 2]
+        else:
+            widths = [g]
+        for w in widths:
+            t = len(panels)
+            panels.append({"t": t, "k0": k0, "k1": k0 + w, "w": w, "a_src": row * pc + k0 // kc, "b_src": (k0 // kr) * pc + col,
+                           "a_mine": k0 // kc == col, "b_mine": k0 // kr == row, "beta": 0.0 if t == 0 else 1.0})
+            k0 += w
     w = g
     return {"mb": mb, "nb": nb, "kr": kr, "kc": kc, "w": w, "row0": row * mb, "col0": col * nb, "panels": panels,
             "gemms": panels}
@@ -123,7 +136,8 @@ class ShardedGemm:
         self.reserve_sms = int(env.get("JB_RESERVE_SMS", "8" if grid.world <= 2 else "16"))
         self.capped_panels = int(env.get("JB_CAPPED_PANELS", "4"))
         self.esz = {"s": 4, "d": 8, "c": 8, "z": 16}[t]
-        self.plan = gemm_plan(n, grid.pr, grid.pc, grid.row, grid.col, chunks=1 if grid.world == 1 else 16)
+        self.mode = env.get("JB_SUMMA", "pull") if grid.world > 1 else "local"
+        self.plan = gemm_plan(n, grid.pr, grid.pc, grid.row, grid.col, chunks=1 if grid.world == 1 else 16, owned_first=self.mode == "pull")
         P = self.plan
         dev = torch.device("cuda", torch.cuda.current_device())
         f64 = getattr(torch, self._TORCH[t])
@@ -139,7 +153,6 @@ class ShardedGemm:
         # ranks of a process row map each other's A slab, those of a process column each other's B slab, and every
         # panel a rank does not own is PULLED from its owner by a copy-engine transfer over NVLink — no collective
         # kernel competes with the persistent GEMM for SMs (round 1 reserved 8-16 SMs for NCCL's broadcast kernels).
-        self.mode = env.get("JB_SUMMA", "pull") if grid.world > 1 else "local"
         elt = self.esz
         if self.mode == "pull":
             from . import _lib
@@ -245,7 +258,7 @@ class ShardedGemm:
         finally:
             self.lib.jb_set_option(b"gemm.max_ctas", 0)
 
-    def _step_pull(self):
+    def _step_pull(self, own_ready=None, peers_ready=None):
         """One distributed product with copy-engine panel pulls: every panel this rank does not own is copied from its
         owner's slab (peer-mapped, NVLink) on one of two side streams, in K order; the local GEMM of a panel waits only
         for its own two copies.  The operands are inputs (nobody writes them during the product), so no rank has to
@@ -254,6 +267,8 @@ class ShardedGemm:
         mb, nb, elt = P["mb"], P["nb"], self.esz
         cur = torch.cuda.current_stream()
         self.s_a.wait_event(self.ev_done); self.s_b.wait_event(self.ev_done)   # the previous product has read its panels
+        if peers_ready is not None:      # end-to-end path: the owners' operands are still arriving from their hosts
+            self.s_a.wait_event(peers_ready); self.s_b.wait_event(peers_ready)
         for p in P["panels"]:
             t = p["t"]
             if not p["a_mine"]:
@@ -270,6 +285,8 @@ class ShardedGemm:
                 cur.wait_event(self.ev_a[t])
             if not p["b_mine"]:
                 cur.wait_event(self.ev_b[t])
+            if own_ready is not None and (p["a_mine"] or p["b_mine"]):
+                cur.wait_event(own_ready[t])
             self._local_gemm(p)
         self.ev_done.record(cur)
 
@@ -355,18 +372,29 @@ class ShardedGemm:
         self.check(lib.jb_memcpy_d2h(hB.data_ptr(), self.B_ptr + b_off, b_bytes), "d2h B")
         dist = grid.dist
         cur = torch.cuda.current_stream()
-        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
-        ev_in, ev_c = torch.cuda.Event(), torch.cuda.Event()
+        s_in, s_out, s_bar = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+        ev_own = [torch.cuda.Event() for _ in P["panels"]]
+        ev_all_in, ev_ready, ev_c = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
         token = torch.zeros(1, device="cuda")
 
         def one():
+            # own operands host -> device in the order the plan consumes them (the first, fully owned granule in four
+            # parts): a local product starts as soon as its own slices are resident
             s_in.wait_stream(cur)
-            self.check(lib.jb_memcpy_async(self.A_ptr + a_off, hA.data_ptr(), a_bytes, s_in.cuda_stream), "h2d A")
-            self.check(lib.jb_memcpy_async(self.B_ptr + b_off, hB.data_ptr(), b_bytes, s_in.cuda_stream), "h2d B")
-            ev_in.record(s_in)
-            cur.wait_event(ev_in)
-            dist.all_reduce(token)                 # every rank's operands are resident: peers may pull
-            self.step()
+            for p in P["panels"]:
+                if p["a_mine"]:
+                    off = p["k0"] * mb * elt
+                    self.check(lib.jb_memcpy_async(self.A_ptr + off, hA.data_ptr() + off - a_off, p["w"] * mb * elt, s_in.cuda_stream), "h2d A")
+                if p["b_mine"]:
+                    off = p["k0"] * nb * elt
+                    self.check(lib.jb_memcpy_async(self.B_ptr + off, hB.data_ptr() + off - b_off, p["w"] * nb * elt, s_in.cuda_stream), "h2d B")
+                ev_own[p["t"]].record(s_in)
+            ev_all_in.record(s_in)
+            s_bar.wait_event(ev_all_in)
+            with torch.cuda.stream(s_bar):
+                dist.all_reduce(token)             # every rank's operands are resident: peers may pull
+                ev_ready.record(s_bar)
+            self._step_pull(own_ready=ev_own, peers_ready=ev_ready)
             ev_c.record(cur)
             s_out.wait_event(ev_c)
             self.check(lib.jb_memcpy_async(hC.data_ptr(), self.C.data_ptr(), c_bytes, s_out.cuda_stream), "d2h C")
@@ -384,8 +412,8 @@ class ShardedGemm:
         ms = float(ms.item())
         return {"value": self.flop / (ms * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": ms,
                 "h2d_bytes_per_step": (a_bytes + b_bytes) * grid.world, "d2h_bytes_per_step": c_bytes * grid.world,
-                "path": "pinned host blocks -> H2D (copy engine) -> barrier -> copy-engine panel pulls over NVLink + cblas_dgemm panels "
-                        "-> D2H of the C block"}
+                "path": "pinned host blocks -> H2D in consumption order (products on owned panels start as they land) -> barrier -> "
+                        "copy-engine panel pulls over NVLink + cblas_dgemm panels -> D2H of the C block"}
 
 
 class ShardedBatchedLU:
@@ -397,7 +425,7 @@ class ShardedBatchedLU:
         import torch
         from ._lib import lib, check
         self.torch, self.lib, self.check = torch, lib, check
-        self.n = n
+        self.n, self.grid = n, grid
         self.start, self.local_batch = split_batch(batch, grid.world, grid.rank)
         dev = torch.device("cuda", torch.cuda.current_device())
         nb = self.local_batch

@@ -31,10 +31,15 @@ def test_gemm_plan_covers_k_exactly():
     n = 64
     for world in (1, 2, 4, 8):
         pr, pc = grid_shape(world)
-        for r in range(world):
-            P = gemm_plan(n, pr, pc, r // pc, r % pc, chunks=8)
-            ks = [(g["k0"], g["k1"]) for g in P["panels"]]
+        for r, owned_first in [(r, o) for r in range(world) for o in (False, True)]:
+            P = gemm_plan(n, pr, pc, r // pc, r % pc, chunks=8, owned_first=owned_first)
+            ks = sorted((g["k0"], g["k1"]) for g in P["panels"])
             assert ks[0][0] == 0 and ks[-1][1] == n and all(a[1] == b[0] for a, b in zip(ks, ks[1:]))
+            if not owned_first:      # the collective path needs the same (ascending) K order on every rank
+                assert ks == [(g["k0"], g["k1"]) for g in P["panels"]]
+            else:                    # the pull path starts with what the rank owns
+                cls = [0 if (g["a_mine"] and g["b_mine"]) else (1 if (g["a_mine"] or g["b_mine"]) else 2) for g in P["panels"]]
+                assert cls == sorted(cls)
             assert P["panels"][0]["beta"] == 0.0 and all(g["beta"] == 1.0 for g in P["panels"][1:])
             for g in P["panels"]:   # a panel never straddles an ownership boundary, and its owners sit in my row / column
                 assert g["k0"] // P["kc"] == (g["k1"] - 1) // P["kc"] and g["k0"] // P["kr"] == (g["k1"] - 1) // P["kr"]
