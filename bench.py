@@ -214,6 +214,7 @@ def verify_columns(np, torch, gemm, ncols):
     Returns (relative Frobenius error, north_star bound 4*n*eps*|A||B|/|C|)."""
     from jalla_b200 import synth
     P, n, t = gemm.plan, gemm.n, gemm.t
+    assert gemm.mode in ("pull", "local"), "verify_columns reads the n x nb column block of the pull / local layouts"
     mb, nb = P["mb"], P["nb"]
     dt = {"s": np.float32, "d": np.float64, "c": np.complex64, "z": np.complex128}[t]
     rng = np.random.default_rng(1000 + gemm.grid.rank)
@@ -224,9 +225,8 @@ def verify_columns(np, torch, gemm, ncols):
     Cs = np.empty((mb, len(cols)), dtype=dt, order="F")
     es = A.itemsize
     col = np.empty(n, dtype=dt)
-    for q, j in enumerate(cols):
-        for p in P["panels"]:      # B panel t is a (w x nb) block with ld = w
-            gemm.check(gemm.lib.jb_memcpy_d2h(col.ctypes.data + p["k0"] * es, gemm.b_ptrs[p["t"]] + int(j) * p["w"] * es, p["w"] * es), "verify d2h B")
+    for q, j in enumerate(cols):       # the B column block is n x nb, column-major, ld = n
+        gemm.check(gemm.lib.jb_memcpy_d2h(col.ctypes.data, gemm.B_ptr + int(j) * n * es, n * es), "verify d2h B")
         Bs[:, q] = col
         gemm.check(gemm.lib.jb_memcpy_d2h(Cs[:, q].ctypes.data, gemm.C.data_ptr() + int(j) * mb * es, mb * es), "verify d2h C")
     # the operands on the device are the generator's (covers the peer pulls): sampled rows of A, all sampled columns of B

@@ -47,6 +47,7 @@ _sig("jb_memcpy_h2d", _i, _p, _p, C.c_size_t)
 _sig("jb_memcpy_d2h", _i, _p, _p, C.c_size_t)
 _sig("jb_memcpy_d2d", _i, _p, _p, C.c_size_t)
 _sig("jb_memcpy_async", _i, _p, _p, C.c_size_t, _p)
+_sig("jb_memcpy2d_async", _i, _p, C.c_size_t, _p, C.c_size_t, C.c_size_t, C.c_size_t, _p)
 _sig("jb_ipc_export", _i, _p, _p)
 _sig("jb_ipc_open", _p, _p)
 _sig("jb_ipc_close", _i, _p)
@@ -118,6 +119,7 @@ for _t in "sdcz":
 _sig("jb_dist_create", _i, C.POINTER(_p), _i, _i, _i)
 _sig("jb_dist_destroy", _i, _p)
 _sig("jb_dist_ngpus", _i, _p)
+_sig("jb_dist_last_ms", _d, _p, _i)
 _sig("jb_dist_dgemm", _i, _p, _i, _i, _i, _i, _i, _d, _p, _i, _p, _i, _d, _p, _i)
 _sig("jb_dist_dgetrf", _i, _p, _i, _p, _i, _p)
 _sig("jb_dist_dgetrs", _i, _p, _c, _i, _i, _p, _i, _p, _p, _i)

@@ -20,6 +20,7 @@
 #include "jb_common.cuh"
 #include <vector>
 #include <algorithm>
+#include <chrono>
 
 namespace jb {
 
@@ -46,6 +47,7 @@ struct Dist {
   int kind = 0;                   // 0 none, 1 LU, 2 Cholesky (lower storage)
   int n = 0, ld = 0;
   const void *host_a = nullptr;
+  double ms[3] = {0, 0, 0};       // last factorisation: host -> devices, factorisation, devices -> host (jb_dist_last_ms)
 };
 
 #define DCHK(call)                                                                                          \
@@ -65,6 +67,7 @@ static int sync_all(Dist *h) {
   }
   return 0;
 }
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 static int nloc_blocks(int nblk, int P, int d) { return nblk > d ? (nblk - d + P - 1) / P : 0; }
 
 static void free_resident(Dist *h) {
@@ -76,11 +79,12 @@ static void free_resident(Dist *h) {
     if (c.ipiv) cudaFree(c.ipiv);
     c.L = nullptr; c.ipiv = nullptr; c.l_bytes = c.p_bytes = 0;
   }
-  h->kind = 0; h->host_a = nullptr;
+  h->kind = 0; h->host_a = nullptr; h->n = 0;
 }
 
 // (re)allocates the block-cyclic storage for an n x n matrix: local columns, two panel buffers, pivots
 static int alloc_resident(Dist *h, int n) {
+  if (h->n == n && !h->d.empty() && h->d[0].L) { h->kind = 0; h->host_a = nullptr; return 0; }     // same shape as last time: keep the buffers
   free_resident(h);
   const int nb = h->nb, nblk = (n + nb - 1) / nb;
   h->n = n; h->ld = n + (n & 1);
@@ -133,7 +137,10 @@ static int gather_cols(Dist *h, double *A, int lda, int n, int) {
 static int dist_getrf(Dist *h, int n, double *A, int lda, int *ipiv, int *info_out) {
   if (int rc = alloc_resident(h, n)) return rc;
   const int nb = h->nb, P = h->P, ld = h->ld, nblk = (n + nb - 1) / nb;
+  double t0 = now_ms();
   if (int rc = scatter_cols(h, A, lda, n)) return rc;
+  if (int rc = sync_all(h)) return rc;
+  h->ms[0] = now_ms() - t0; t0 = now_ms();
   std::vector<cudaEvent_t> ev_panel(nblk), ev_first(nblk);
   std::vector<std::vector<cudaEvent_t>> ev_recv(P, std::vector<cudaEvent_t>(nblk)), ev_upd(P, std::vector<cudaEvent_t>(nblk));
   int *d_panel_info = nullptr;
@@ -225,6 +232,7 @@ static int dist_getrf(Dist *h, int n, double *A, int lda, int *ipiv, int *info_o
     }
   }
   if (!rc) rc = sync_all(h);
+  h->ms[1] = now_ms() - t0; t0 = now_ms();
   int info = 0;
   if (!rc) {
     // the first zero pivot over all panels: each owner kept the first of ITS panels
@@ -246,7 +254,8 @@ static int dist_getrf(Dist *h, int n, double *A, int lda, int *ipiv, int *info_o
     DevGuard g(h->d[q].dev);
     cudaFree(h->d[q].info); h->d[q].info = nullptr;
   }
-  if (rc) { free_resident(h); return rc; }
+  h->ms[2] = now_ms() - t0;
+  if (rc) { free_resident(h); h->n = 0; return rc; }
   h->kind = 1; h->host_a = A;
   *info_out = info;
   return 0;
@@ -583,6 +592,8 @@ int jb_dist_destroy(void *handle) {
   return 0;
 }
 int jb_dist_ngpus(void *handle) { return handle ? ((Dist *)handle)->P : 0; }
+// wall-clock phases of the last jb_dist_dgetrf / dpotrf: 0 host -> devices, 1 factorisation (all devices), 2 devices -> host
+double jb_dist_last_ms(void *handle, int phase) { return (handle && phase >= 0 && phase < 3) ? ((Dist *)handle)->ms[phase] : -1.0; }
 
 int jb_dist_dgemm(void *handle, int transa, int transb, int m, int n, int k, double alpha, const double *a, int lda, const double *b, int ldb,
                   double beta, double *c, int ldc) {
@@ -632,12 +643,17 @@ int jb_dist_dpotrf(void *handle, char uplo, int n, double *a, int lda) {
   if (lda < std::max(1, n)) return -5;
   if (n == 0) return 0;
   if (int rc = alloc_resident(h, n)) return rc;
+  double t0 = now_ms();
   if (int rc = scatter_cols(h, a, lda, n)) return rc;
+  if (int rc = sync_all(h)) return rc;
+  h->ms[0] = now_ms() - t0; t0 = now_ms();
   int info = 0;
   if (int rc = dist_potrf(h, n, &info)) { free_resident(h); return rc; }
+  h->ms[1] = now_ms() - t0; t0 = now_ms();
   // the device columns still hold the caller's strictly upper triangle (never written), so whole columns go back
   if (int rc = gather_cols(h, a, lda, n, 0)) return rc;
   if (int rc = sync_all(h)) return rc;
+  h->ms[2] = now_ms() - t0;
   h->kind = 2; h->host_a = a;
   return info;
 }

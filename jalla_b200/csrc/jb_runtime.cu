@@ -248,6 +248,12 @@ int jb_memcpy_async(void *dst, const void *src, size_t bytes, void *cuda_stream)
   JB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)cuda_stream));
   return 0;
 }
+// 2-D form: `height` rows of `width_bytes`, pitches in bytes (a K panel of a column-major block is a strided sub-matrix)
+int jb_memcpy2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width_bytes, size_t height, void *cuda_stream) {
+  if (int rc = ensure_device()) return rc;
+  JB_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width_bytes, height, cudaMemcpyDefault, (cudaStream_t)cuda_stream));
+  return 0;
+}
 void jb_set_stream(void *s) { tls().stream = (cudaStream_t)s; }
 void *jb_get_stream(void) { return (void *)tls().stream; }
 uint64_t jb_kernel_launches(void) { return g_launches.load(); }

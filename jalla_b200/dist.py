@@ -58,45 +58,49 @@ class ProcessGrid:
                     self.col_group = g
 
 
-def gemm_plan(n: int, pr: int, pc: int, row: int, col: int, chunks: int = 16, owned_first: bool = False):
+def gemm_plan(n: int, pr: int, pc: int, row: int, col: int, chunks: int = 16, owned_first: bool = False, split_owned: bool = False):
     """Static description of rank (row,col)'s share of C = A*B (all sizes in elements).
-    K is cut into panels that never straddle an owner's K block; panel [k0,k1) of A lives on process column k0//kc
-    and of B on process row k0//kr.  Each panel is one broadcast and one local GEMM,
-    so only the first panel's transfer is exposed; everything else hides under the DMMA GEMMs."""
-    assert n % pr == 0 and n % pc == 0, "N must divide the process grid"
-    mb, nb, kr, kc = n // pr, n // pc, n // pr, n // pc
-    # panels may not straddle an ownership boundary (multiples of kr for B, of kc for A): K is cut into granules of
-    # g = min(kr, kc) columns.  A rank starts with the granules whose operands it already holds (both, then one of
-    # them) while the others are on their way; only the FIRST granule is cut finer — in four equal parts when the rank
-    # owns both operands (the end-to-end path streams them from the host in that order), geometrically
-    # (g/8, g/8, g/4, g/2) when its first product has to wait for a transfer — so that there are few C read-modify-write
-    # sweeps and the exposed first transfer is small.  (The K order differs per rank: C agrees to rounding, not bit for bit.)
-    g = min(kr, kc)
-    assert kr % g == 0 and kc % g == 0
+
+    K is cut into pc granules of g = n/pc columns (pr divides pc on the grids used: 1x2, 2x2, 2x4).  Ownership is SKEWED
+    like Cannon's initial alignment, so that every rank holds one granule of BOTH operands and can start multiplying
+    without waiting for anybody: with r = pc/pr,
+        A[row block i, granule q]   lives on process column (q - i*r) mod pc   -> rank (i,j) owns A granule (j + i*r) mod pc,
+        B[granule q, column block j] lives on process row   ((q - j) mod pc) // r -> rank (i,j) owns B granules (j + i*r + 0..r-1) mod pc.
+    A panel is one transfer and one local GEMM.  owned_first (the pull path): the rank's own granule first, then those it
+    holds one operand of, then the rest; collectives (the NCCL / gloo path) need the same ascending order on every rank.
+    The first granule is cut finer only where that helps: geometrically (g/8, g/8, g/4, g/2) when the first product has to
+    wait for a transfer, in four equal parts when split_owned (the end-to-end path streams the own operands from the host
+    in that order).  The K order differs per rank: C agrees to rounding, not bit for bit."""
+    assert n % pr == 0 and n % pc == 0 and pc % pr == 0, "N must divide the process grid (and Pr must divide Pc)"
+    mb, nb = n // pr, n // pc
+    g, r, G = n // pc, pc // pr, pc
+    a_col = lambda i, q: (q - i * r) % pc                 # process column owning A[i, q]
+    b_row = lambda q, j: ((q - j) % pc) // r              # process row owning B[q, j]
     granules = []
-    for q in range(n // g):
-        k0 = q * g
-        a_mine, b_mine = k0 // kc == col, k0 // kr == row
+    for q in range(G):
+        a_mine, b_mine = a_col(row, q) == col, b_row(q, col) == row
         granules.append((0 if (a_mine and b_mine) else (1 if (a_mine or b_mine) else 2), q))
-    if owned_first and chunks > 1 and pr * pc > 1:
-        granules.sort()              # only for the pull path: collectives need the same panel order on every rank
+    multi = pr * pc > 1
+    if owned_first and chunks > 1 and multi:
+        granules.sort()
     else:
-        granules = [(1, q) for _, q in granules]
+        granules = [(1 if multi else 0, q) for _, q in granules]
     panels = []
     for idx, (cls, q) in enumerate(granules):
         k0 = q * g
-        if idx == 0 and chunks > 1 and pr * pc > 1 and g % 8 == 0:
-            widths = [g // 4] * 4 if cls == 0 else [g // 8, g // 8, g // 4, g // 2]
-        else:
-            widths = [g]
+        widths = [g]
+        if idx == 0 and chunks > 1 and multi and g % 8 == 0:
+            if cls == 0 and split_owned:
+                widths = [g // 4] * 4
+            elif cls != 0:
+                widths = [g // 8, g // 8, g // 4, g // 2]
         for w in widths:
             t = len(panels)
-            panels.append({"t": t, "k0": k0, "k1": k0 + w, "w": w, "a_src": row * pc + k0 // kc, "b_src": (k0 // kr) * pc + col,
-                           "a_mine": k0 // kc == col, "b_mine": k0 // kr == row, "beta": 0.0 if t == 0 else 1.0})
+            a_src, b_src = row * pc + a_col(row, q), b_row(q, col) * pc + col
+            panels.append({"t": t, "k0": k0, "k1": k0 + w, "w": w, "a_src": a_src, "b_src": b_src,
+                           "a_mine": a_src == row * pc + col, "b_mine": b_src == row * pc + col, "beta": 0.0 if t == 0 else 1.0})
             k0 += w
-    w = g
-    return {"mb": mb, "nb": nb, "kr": kr, "kc": kc, "w": w, "row0": row * mb, "col0": col * nb, "panels": panels,
-            "gemms": panels}
+    return {"mb": mb, "nb": nb, "g": g, "w": g, "row0": row * mb, "col0": col * nb, "panels": panels, "gemms": panels}
 
 
 def summa_step(plan, grid: ProcessGrid, a_panels, b_panels, local_gemm):
@@ -138,6 +142,8 @@ class ShardedGemm:
         self.esz = {"s": 4, "d": 8, "c": 8, "z": 16}[t]
         self.mode = env.get("JB_SUMMA", "pull") if grid.world > 1 else "local"
         self.plan = gemm_plan(n, grid.pr, grid.pc, grid.row, grid.col, chunks=1 if grid.world == 1 else 16, owned_first=self.mode == "pull")
+        # same buffers, finer first granule: the end-to-end path streams the own operands from the host in this order
+        self.plan_e2e = gemm_plan(n, grid.pr, grid.pc, grid.row, grid.col, chunks=1 if grid.world == 1 else 16, owned_first=self.mode == "pull", split_owned=True)
         P = self.plan
         dev = torch.device("cuda", torch.cuda.current_device())
         f64 = getattr(torch, self._TORCH[t])
@@ -148,7 +154,8 @@ class ShardedGemm:
         else:   # complex scalars travel by pointer (BlasOps.hs:156,180): [1, 0, 1] -> alpha, beta=0, beta=1
             self._scal = np.array([1.0, 0.0, 1.0], dtype=np.complex64 if t == "c" else np.complex128)
         # column-major blocks held as flat device buffers: A row block mb x n (ld = mb; a K panel is a contiguous
-        # slice), B as one w x nb region per K panel (ld = w) inside one n x nb slab (panel t at element k0 * nb).
+        # slice) and B column block n x nb (ld = n; a K panel is a row range, i.e. a strided sub-matrix) — layouts that
+        # do not depend on how a rank cuts K into panels, because peers read each other's blocks.
         # With more than one rank the two slabs come from jb_malloc (plain cudaMalloc, exportable over CUDA IPC): the
         # ranks of a process row map each other's A slab, those of a process column each other's B slab, and every
         # panel a rank does not own is PULLED from its owner by a copy-engine transfer over NVLink — no collective
@@ -165,10 +172,11 @@ class ShardedGemm:
             self._B_slab = torch.empty(n * nb, dtype=f64, device=dev)
             self.A_ptr, self.B_ptr = self.A_row.data_ptr(), self._B_slab.data_ptr()
         self.a_ptrs = [self.A_ptr + p["k0"] * mb * elt for p in P["panels"]]
-        self.b_ptrs = [self.B_ptr + p["k0"] * nb * elt for p in P["panels"]]
+        self.b_ptrs = [self.B_ptr + p["k0"] * elt for p in P["panels"]]
+        self.ldb = n
         if self.mode != "pull":
             self.a_panels = [self.A_row[p["k0"] * mb:p["k1"] * mb] for p in P["panels"]]
-            self.b_panels = [self._B_slab[p["k0"] * nb:p["k1"] * nb] for p in P["panels"]]
+            self.b_panels = None      # (the collective path keeps its own contiguous panel tensors, see step())
         self.C = torch.empty(mb * nb, dtype=f64, device=dev)
         # generate only the panels this rank OWNS; the rest arrives from its owner
         fill = getattr(lib, f"jb_{t}fill_uniform")
@@ -177,7 +185,7 @@ class ShardedGemm:
             if p["a_mine"]:
                 check(fill(self.a_ptrs[p["t"]], mb, mb, p["w"], P["row0"], p["k0"], seed, *extra), "fill A")
             if p["b_mine"]:
-                check(fill(self.b_ptrs[p["t"]], p["w"], p["w"], nb, p["k0"], P["col0"], seed + 1, *extra), "fill B")
+                check(fill(self.b_ptrs[p["t"]], n, p["w"], nb, p["k0"], P["col0"], seed + 1, *extra), "fill B")
         torch.cuda.synchronize()
         if self.mode == "pull":
             self._open_peers()
@@ -203,8 +211,8 @@ class ShardedGemm:
                 ptr = lib.jb_ipc_open(raw[64:]); assert ptr, lib.jb_last_error_string()
                 self.peer_b[r] = ptr; self._mapped.append(ptr)
         self.s_a, self.s_b = torch.cuda.Stream(), torch.cuda.Stream()
-        self.ev_a = [torch.cuda.Event() for _ in self.plan["panels"]]
-        self.ev_b = [torch.cuda.Event() for _ in self.plan["panels"]]
+        self.ev_a = [torch.cuda.Event() for _ in self.plan_e2e["panels"]]
+        self.ev_b = [torch.cuda.Event() for _ in self.plan_e2e["panels"]]
         self.ev_done = torch.cuda.Event()
         self.ev_done.record(torch.cuda.current_stream())
         grid.dist.barrier()
@@ -226,15 +234,18 @@ class ShardedGemm:
     def flop(self) -> float:
         return (8.0 if self.t in "cz" else 2.0) * float(self.n) ** 3
 
-    def _local_gemm(self, p):
-        P = self.plan
+    def _local_gemm(self, p, P=None):
+        P = P or self.plan
         if self._scal is None:
             al, be = 1.0, p["beta"]
         else:
             base, isz = self._scal.ctypes.data, self._scal.itemsize
             al, be = base, base + (2 * isz if p["beta"] else isz)
-        self._gemm(102, 111, 111, P["mb"], P["nb"], p["w"], al, self.a_ptrs[p["t"]], P["mb"],
-                   self.b_ptrs[p["t"]], p["w"], be, self.C.data_ptr(), P["mb"])
+        if getattr(self, "ldb_panels", False):       # collective path: contiguous panel tensors
+            a_ptr, b_ptr, ldb = self.a_ptrs[p["t"]], self.b_ptrs[p["t"]], p["w"]
+        else:
+            a_ptr, b_ptr, ldb = self.A_ptr + p["k0"] * P["mb"] * self.esz, self.B_ptr + p["k0"] * self.esz, self.ldb
+        self._gemm(102, 111, 111, P["mb"], P["nb"], p["w"], al, a_ptr, P["mb"], b_ptr, ldb, be, self.C.data_ptr(), P["mb"])
 
     def step(self):
         P, grid = self.plan, self.grid
@@ -253,17 +264,26 @@ class ShardedGemm:
         def gemm(p):
             self.lib.jb_set_option(b"gemm.max_ctas", max(nsm - self.reserve_sms, 1) if p["t"] < n_capped else 0)
             self._local_gemm(p)
+        if self.b_panels is None:     # contiguous receive buffers for the broadcasts; owned panels are packed into them
+            f64 = getattr(self.torch, self._TORCH[self.t])
+            self.b_panels = [self.torch.empty(p["w"] * P["nb"], dtype=f64, device=self.C.device) for p in P["panels"]]
+            for p in P["panels"]:
+                if p["b_mine"]:
+                    self.check(self.lib.jb_memcpy2d_async(self.b_panels[p["t"]].data_ptr(), p["w"] * self.esz, self.b_ptrs[p["t"]], self.n * self.esz,
+                                                          p["w"] * self.esz, P["nb"], self.torch.cuda.current_stream().cuda_stream), "pack B")
+            self.b_ptrs = [t.data_ptr() for t in self.b_panels]
+            self.ldb_panels = True
         try:
             summa_step(P, grid, self.a_panels, self.b_panels, gemm)
         finally:
             self.lib.jb_set_option(b"gemm.max_ctas", 0)
 
-    def _step_pull(self, own_ready=None, peers_ready=None):
+    def _step_pull(self, own_ready=None, peers_ready=None, plan=None):
         """One distributed product with copy-engine panel pulls: every panel this rank does not own is copied from its
         owner's slab (peer-mapped, NVLink) on one of two side streams, in K order; the local GEMM of a panel waits only
         for its own two copies.  The operands are inputs (nobody writes them during the product), so no rank has to
         wait for another: the only cross-rank ordering is the barrier around the timed region."""
-        torch, lib, P = self.torch, self.lib, self.plan
+        torch, lib, P = self.torch, self.lib, plan or self.plan
         mb, nb, elt = P["mb"], P["nb"], self.esz
         cur = torch.cuda.current_stream()
         self.s_a.wait_event(self.ev_done); self.s_b.wait_event(self.ev_done)   # the previous product has read its panels
@@ -276,8 +296,8 @@ class ShardedGemm:
                 self.check(lib.jb_memcpy_async(self.A_ptr + off, self.peer_a[p["a_src"]] + off, p["w"] * mb * elt, self.s_a.cuda_stream), "pull A")
                 self.ev_a[t].record(self.s_a)
             if not p["b_mine"]:
-                off = p["k0"] * nb * elt
-                self.check(lib.jb_memcpy_async(self.B_ptr + off, self.peer_b[p["b_src"]] + off, p["w"] * nb * elt, self.s_b.cuda_stream), "pull B")
+                off, pitch = p["k0"] * elt, self.n * elt
+                self.check(lib.jb_memcpy2d_async(self.B_ptr + off, pitch, self.peer_b[p["b_src"]] + off, pitch, p["w"] * elt, nb, self.s_b.cuda_stream), "pull B")
                 self.ev_b[t].record(self.s_b)
         for p in P["panels"]:
             t = p["t"]
@@ -287,7 +307,7 @@ class ShardedGemm:
                 cur.wait_event(self.ev_b[t])
             if own_ready is not None and (p["a_mine"] or p["b_mine"]):
                 cur.wait_event(own_ready[t])
-            self._local_gemm(p)
+            self._local_gemm(p, P)
         self.ev_done.record(cur)
 
     def kernel_ms(self, reps=3) -> float:
@@ -362,14 +382,25 @@ class ShardedGemm:
         # (copy engine), a barrier tells the peers they may pull, the distributed product runs, and the C block goes
         # device -> host.  A second barrier after the product keeps the next step's H2D from overwriting panels a peer
         # is still pulling.
-        mb, nb, kr, kc, elt = P["mb"], P["nb"], P["kr"], P["kc"], self.esz
-        a_off, a_bytes = grid.col * kc * mb * elt, kc * mb * elt
-        b_off, b_bytes = grid.row * kr * nb * elt, kr * nb * elt
+        P = self.plan_e2e
+        mb, nb, elt = P["mb"], P["nb"], self.esz
+        # pinned host copies of the panels this rank owns, packed in the order the plan consumes them
+        a_host, b_host, a_bytes, b_bytes = {}, {}, 0, 0
+        for p in P["panels"]:
+            if p["a_mine"]:
+                a_host[p["t"]] = a_bytes; a_bytes += p["w"] * mb * elt
+            if p["b_mine"]:
+                b_host[p["t"]] = b_bytes; b_bytes += p["w"] * nb * elt
         c_bytes = mb * nb * elt
-        hA = torch.empty(a_bytes, dtype=torch.uint8, pin_memory=True); hB = torch.empty(b_bytes, dtype=torch.uint8, pin_memory=True)
+        hA = torch.empty(max(a_bytes, 16), dtype=torch.uint8, pin_memory=True); hB = torch.empty(max(b_bytes, 16), dtype=torch.uint8, pin_memory=True)
         hC = torch.empty(c_bytes, dtype=torch.uint8, pin_memory=True)
-        self.check(lib.jb_memcpy_d2h(hA.data_ptr(), self.A_ptr + a_off, a_bytes), "d2h A")
-        self.check(lib.jb_memcpy_d2h(hB.data_ptr(), self.B_ptr + b_off, b_bytes), "d2h B")
+        cs = torch.cuda.current_stream().cuda_stream
+        for p in P["panels"]:
+            if p["a_mine"]:
+                self.check(lib.jb_memcpy_async(hA.data_ptr() + a_host[p["t"]], self.A_ptr + p["k0"] * mb * elt, p["w"] * mb * elt, cs), "d2h A")
+            if p["b_mine"]:      # compact host panel (w x nb, ld = w)
+                self.check(lib.jb_memcpy2d_async(hB.data_ptr() + b_host[p["t"]], p["w"] * elt, self.B_ptr + p["k0"] * elt, n * elt, p["w"] * elt, nb, cs), "d2h B")
+        torch.cuda.synchronize()
         dist = grid.dist
         cur = torch.cuda.current_stream()
         s_in, s_out, s_bar = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
@@ -378,23 +409,22 @@ class ShardedGemm:
         token = torch.zeros(1, device="cuda")
 
         def one():
-            # own operands host -> device in the order the plan consumes them (the first, fully owned granule in four
-            # parts): a local product starts as soon as its own slices are resident
+            # own operands host -> device in the order the plan consumes them (the own granule first, in four parts): a
+            # local product starts as soon as its slices are resident
             s_in.wait_stream(cur)
             for p in P["panels"]:
                 if p["a_mine"]:
-                    off = p["k0"] * mb * elt
-                    self.check(lib.jb_memcpy_async(self.A_ptr + off, hA.data_ptr() + off - a_off, p["w"] * mb * elt, s_in.cuda_stream), "h2d A")
+                    self.check(lib.jb_memcpy_async(self.A_ptr + p["k0"] * mb * elt, hA.data_ptr() + a_host[p["t"]], p["w"] * mb * elt, s_in.cuda_stream), "h2d A")
                 if p["b_mine"]:
-                    off = p["k0"] * nb * elt
-                    self.check(lib.jb_memcpy_async(self.B_ptr + off, hB.data_ptr() + off - b_off, p["w"] * nb * elt, s_in.cuda_stream), "h2d B")
+                    self.check(lib.jb_memcpy2d_async(self.B_ptr + p["k0"] * elt, n * elt, hB.data_ptr() + b_host[p["t"]], p["w"] * elt,
+                                                     p["w"] * elt, nb, s_in.cuda_stream), "h2d B")
                 ev_own[p["t"]].record(s_in)
             ev_all_in.record(s_in)
             s_bar.wait_event(ev_all_in)
             with torch.cuda.stream(s_bar):
                 dist.all_reduce(token)             # every rank's operands are resident: peers may pull
                 ev_ready.record(s_bar)
-            self._step_pull(own_ready=ev_own, peers_ready=ev_ready)
+            self._step_pull(own_ready=ev_own, peers_ready=ev_ready, plan=P)
             ev_c.record(cur)
             s_out.wait_event(ev_c)
             self.check(lib.jb_memcpy_async(hC.data_ptr(), self.C.data_ptr(), c_bytes, s_out.cuda_stream), "d2h C")

@@ -41,10 +41,26 @@ def test_gemm_plan_covers_k_exactly():
                 cls = [0 if (g["a_mine"] and g["b_mine"]) else (1 if (g["a_mine"] or g["b_mine"]) else 2) for g in P["panels"]]
                 assert cls == sorted(cls)
             assert P["panels"][0]["beta"] == 0.0 and all(g["beta"] == 1.0 for g in P["panels"][1:])
-            for g in P["panels"]:   # a panel never straddles an ownership boundary, and its owners sit in my row / column
-                assert g["k0"] // P["kc"] == (g["k1"] - 1) // P["kc"] and g["k0"] // P["kr"] == (g["k1"] - 1) // P["kr"]
+            for g in P["panels"]:   # a panel never straddles a granule, and its owners sit in my row / column
+                assert g["k0"] // P["g"] == (g["k1"] - 1) // P["g"]
                 assert g["a_src"] // pc == r // pc and g["b_src"] % pc == r % pc
                 assert g["a_mine"] == (g["a_src"] == r) and g["b_mine"] == (g["b_src"] == r)
+            # skewed ownership: every rank owns one granule of BOTH operands, and it comes first on the pull path
+            both = [g for g in P["panels"] if g["a_mine"] and g["b_mine"]]
+            assert sum(g["w"] for g in both) == P["g"]
+            if owned_first and world > 1:
+                assert P["panels"][0]["a_mine"] and P["panels"][0]["b_mine"]
+        # every (row block, granule) of A and (granule, column block) of B has exactly one owner
+        owners_a, owners_b = {}, {}
+        for r in range(world):
+            P = gemm_plan(n, pr, pc, r // pc, r % pc, chunks=1)
+            for g in P["panels"]:
+                if g["a_mine"]:
+                    owners_a.setdefault((r // pc, g["k0"]), []).append(r)
+                if g["b_mine"]:
+                    owners_b.setdefault((g["k0"], r % pc), []).append(r)
+        assert all(len(v) == 1 for v in owners_a.values()) and len(owners_a) == pr * pc
+        assert all(len(v) == 1 for v in owners_b.values()) and len(owners_b) == pc * pc
 
 
 def _worker(rank, world, port, n, q):
