@@ -532,6 +532,154 @@ lu32q_kernel(double *__restrict__ Ag, long long stride_a, int *__restrict__ ipiv
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Block-of-four variant (lane = row, one system per warp).  The kernels above pay ~4.4 LSU cycles for every 128-bit
+// shared-memory store although only the pivot lane's predicate is on (tools/smem_probe.cu) — the row publication is the
+// largest item on the saturated pipe (profiles/lu32_r2_notes.md).  Here NOBODY publishes a pivot row.  Once per block
+// of four elimination steps every lane stores what is left of its own row (columns right of the block and the
+// right-hand side): the same store instruction now carries 32 rows instead of one.  The four steps of the block touch
+// only the block's own columns — pivot value, interchange position and the pivot row's (at most three) block entries
+// travel by shfl.idx from the pivot lane, which the ballot of the search already names.  After the block every lane
+// reads the four pivot rows AS THEY STOOD BEFORE THE BLOCK (broadcast 128-bit loads), rebuilds the rows of U with the
+// multipliers lambda(a,b) = l(pivot lane a, step b) —
+//     u0 = r0, u1 = fma(-l10,u0,r1), u2 = fma(-l21,u1,fma(-l20,u0,r2)), u3 = fma(-l32,u2,fma(-l31,u1,fma(-l30,u0,r3)))
+// which are the very operations the pivot lanes perform on their own registers — and applies the four updates in step
+// order, a_ij = fma(-l3,u3,fma(-l2,u2,fma(-l1,u1,fma(-l0,u0,a_ij)))): bit-identical to the one-step-at-a-time sequence.
+// Row stores per system: 64 full-warp instructions instead of 136 one-lane ones; the header stores and loads of the
+// pair kernel become 36 shuffles per block; the back substitution broadcasts x_k by shuffle as well.
+constexpr int B_LD = 34;                    // doubles per stored row: 32 columns, rhs, pad -> 272-byte row stride, so the
+constexpr int B_BYTES = 32 * B_LD * 8;      // 128-bit stores of 8 consecutive lanes cover all 32 banks once
+
+__device__ __forceinline__ void sts2(double *p, double x, double y) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "d"(x), "d"(y) : "memory");
+}
+__device__ __forceinline__ double2 lds2(const double *p) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+  return v;
+}
+
+template <int MODE, int KB>
+__device__ __forceinline__ void lu32b_block(double (&a)[N32], double &bb, double &my_rinv, int &pos, int &dm, int &ip, int &bad,
+                                            double *rows, const int lane) {
+  constexpr unsigned RLO = 64u << 20, RSPAN = ((1981u - 64u) << 20) - 1u;
+  constexpr int KE = KB + 4;                 // first column right of the block
+  double *const mine = rows + lane * B_LD;
+#pragma unroll
+  for (int j = KE; j < N32; j += 2) sts2(&mine[j], a[j], a[j + 1]);
+  if (MODE != 0) mine[N32] = bb;
+  double l[4];
+  int src[4];
+#pragma unroll
+  for (int jj = 0; jj < 4; jj++) {
+    constexpr int k0 = KB;
+    const int k = k0 + jj;
+    const int hk = (__double2hiint(a[k]) & 0x7fffffff) | dm;
+    const int M = __reduce_max_sync(0xffffffffu, hk);
+    const bool c = hk == M;
+    const unsigned ball = __ballot_sync(0xffffffffu, c);
+    bad |= ((ball & (ball - 1u)) != 0u) | ((unsigned)M - RLO > RSPAN);
+    src[jj] = __ffs(ball) - 1;
+    const double rk = rcp_fast(a[k]);
+    const double rinv = __shfl_sync(0xffffffffu, rk, src[jj]);
+    const int ppos = __shfl_sync(0xffffffffu, pos, src[jj]);
+    if (lane == k) ip = ppos + 1;
+    pos = c ? k : (pos == k ? ppos : pos);
+    dm = c ? -1 : dm;
+    if (MODE != 0) my_rinv = dsel(c, rk, my_rinv);
+    const bool act = dm == 0;
+    const double t = __dmul_rn(a[k], rinv);
+    a[k] = dsel(act, t, a[k]);
+    l[jj] = dsel(act, t, 0.0);
+#pragma unroll
+    for (int m = jj + 1; m < 4; m++) {
+      const double u = __shfl_sync(0xffffffffu, a[k0 + m], src[jj]);
+      a[k0 + m] = __fma_rn(-l[jj], u, a[k0 + m]);
+    }
+  }
+  if (KE < N32 || MODE != 0) {
+    const double l10 = __shfl_sync(0xffffffffu, l[0], src[1]);
+    const double l20 = __shfl_sync(0xffffffffu, l[0], src[2]), l21 = __shfl_sync(0xffffffffu, l[1], src[2]);
+    const double l30 = __shfl_sync(0xffffffffu, l[0], src[3]), l31 = __shfl_sync(0xffffffffu, l[1], src[3]), l32 = __shfl_sync(0xffffffffu, l[2], src[3]);
+    const double *const r0 = rows + src[0] * B_LD, *const r1 = rows + src[1] * B_LD, *const r2 = rows + src[2] * B_LD, *const r3 = rows + src[3] * B_LD;
+    __syncwarp();
+#pragma unroll
+    for (int j = KE; j < N32; j += 2) {
+      const double2 u0 = lds2(&r0[j]), v1 = lds2(&r1[j]), v2 = lds2(&r2[j]), v3 = lds2(&r3[j]);
+      const double u1x = __fma_rn(-l10, u0.x, v1.x), u1y = __fma_rn(-l10, u0.y, v1.y);
+      const double u2x = __fma_rn(-l21, u1x, __fma_rn(-l20, u0.x, v2.x)), u2y = __fma_rn(-l21, u1y, __fma_rn(-l20, u0.y, v2.y));
+      const double u3x = __fma_rn(-l32, u2x, __fma_rn(-l31, u1x, __fma_rn(-l30, u0.x, v3.x)));
+      const double u3y = __fma_rn(-l32, u2y, __fma_rn(-l31, u1y, __fma_rn(-l30, u0.y, v3.y)));
+      a[j] = __fma_rn(-l[3], u3x, __fma_rn(-l[2], u2x, __fma_rn(-l[1], u1x, __fma_rn(-l[0], u0.x, a[j]))));
+      a[j + 1] = __fma_rn(-l[3], u3y, __fma_rn(-l[2], u2y, __fma_rn(-l[1], u1y, __fma_rn(-l[0], u0.y, a[j + 1]))));
+    }
+    if (MODE != 0) {
+      const double y0 = r0[N32];
+      const double y1 = __fma_rn(-l10, y0, r1[N32]);
+      const double y2 = __fma_rn(-l21, y1, __fma_rn(-l20, y0, r2[N32]));
+      const double y3 = __fma_rn(-l32, y2, __fma_rn(-l31, y1, __fma_rn(-l30, y0, r3[N32])));
+      bb = __fma_rn(-l[3], y3, __fma_rn(-l[2], y2, __fma_rn(-l[1], y1, __fma_rn(-l[0], y0, bb))));
+    }
+    __syncwarp();
+  }
+}
+template <int MODE, int KB> struct Lu32bBlocks {
+  static __device__ __forceinline__ void run(double (&a)[N32], double &bb, double &my_rinv, int &pos, int &dm, int &ip, int &bad, double *rows, const int lane) {
+    lu32b_block<MODE, KB>(a, bb, my_rinv, pos, dm, ip, bad, rows, lane);
+    Lu32bBlocks<MODE, KB + 4>::run(a, bb, my_rinv, pos, dm, ip, bad, rows, lane);
+  }
+};
+template <int MODE> struct Lu32bBlocks<MODE, N32> {
+  static __device__ __forceinline__ void run(double (&)[N32], double &, double &, int &, int &, int &, int &, double *, int) {}
+};
+
+template <int MODE, int WARPS, int MINB>
+__global__ void __launch_bounds__(32 * WARPS, MINB)
+lu32b_kernel(double *__restrict__ Ag, long long stride_a, int *__restrict__ ipiv_g, double *__restrict__ Bg, long long stride_b,
+             double *__restrict__ Xg, long long stride_x, int *__restrict__ info_g, int *__restrict__ redo, int nsys) {
+  extern __shared__ __align__(16) unsigned char smem_dyn[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double *const rows = reinterpret_cast<double *>(smem_dyn + warp * B_BYTES);
+  for (long long g0 = (long long)blockIdx.x * WARPS; g0 < nsys; g0 += (long long)gridDim.x * WARPS) {
+    long long sys = g0 + warp;
+    if (sys >= nsys) sys = nsys - 1;          // a surplus warp repeats the last system (same values rewritten)
+    double *const A = Ag + sys * stride_a;
+    double a[N32], bb = 0.0, my_rinv = 0.0;
+#pragma unroll
+    for (int j = 0; j < N32; j++) a[j] = __ldcs(A + lane + N32 * j);
+    if (MODE != 0) bb = __ldcs(Bg + sys * stride_b + lane);
+    int pos = lane, dm = 0, bad = 0, ip = 0;
+    Lu32bBlocks<MODE, 0>::run(a, bb, my_rinv, pos, dm, ip, bad, rows, lane);
+    const unsigned badm = __ballot_sync(0xffffffffu, bad);
+    double myx = 0.0;
+    if (MODE != 0) {
+      // back substitution, column sweep on the implicitly permuted U; x_k = y_k * (1/u_kk) leaves the lane at position k by shuffle
+#pragma unroll
+      for (int k = N32 - 1; k >= 0; k--) {
+        const double xc = __dmul_rn(bb, my_rinv);
+        const bool own = pos == k;
+        const int o = __ffs(__ballot_sync(0xffffffffu, own)) - 1;
+        const double xk = __shfl_sync(0xffffffffu, xc, o);
+        myx = dsel(own, xc, myx);
+        bb = __fma_rn(-a[k], xk, bb);
+      }
+    }
+    if (badm == 0) {
+      if (MODE != 2) {
+#pragma unroll
+        for (int j = 0; j < N32; j++) __stcs(A + pos + N32 * j, a[j]);
+        ipiv_g[sys * N32 + lane] = ip;
+      }
+      if (MODE == 1) Bg[sys * stride_b + pos] = myx;
+      if (MODE == 2) Xg[sys * stride_x + pos] = myx;
+      if (lane == 0 && info_g) info_g[sys] = 0;
+    } else if (lane == 0 && g0 + warp < nsys) {
+      redo[1 + atomicAdd(redo, 1)] = (int)sys;
+    }
+    __syncwarp();
+  }
+}
+
 // The exact one-warp routine on the systems the fast kernel flagged.
 template <int MODE>
 __global__ void __launch_bounds__(32 * WARPS_PER_CTA, 4)
@@ -553,6 +701,15 @@ static void launch_q(double *a, long long sa, int *ipiv, double *b, long long sb
   const long ctas = (nsys + WARPS - 1) / WARPS, cap = (long)num_sms() * (lim > 0 && lim < MINB ? lim : MINB);
   lu32q_kernel<MODE, WARPS, MINB, REALIGN, IOV><<<(int)(ctas < cap ? ctas : cap), 32 * WARPS, 0, s>>>(a, sa, ipiv, b, sb, x, sx, info, redo, nsys);
   count_launch();
+}
+template <int MODE, int WARPS, int MINB>
+static int launch_b(double *a, long long sa, int *ipiv, double *b, long long sb, double *x, long long sx, int *info, int *redo, int nsys, cudaStream_t s) {
+  JB_ONCE_PER_DEVICE(JB_CUDA(cudaFuncSetAttribute(lu32b_kernel<MODE, WARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, WARPS * B_BYTES)));
+  const int lim = option("lu32.ctas_per_sm");
+  const long ctas = (nsys + WARPS - 1) / WARPS, cap = (long)num_sms() * (lim > 0 && lim < MINB ? lim : MINB);
+  lu32b_kernel<MODE, WARPS, MINB><<<(int)(ctas < cap ? ctas : cap), 32 * WARPS, WARPS * B_BYTES, s>>>(a, sa, ipiv, b, sb, x, sx, info, redo, nsys);
+  count_launch();
+  return 0;
 }
 template <int S, int MODE, int WARPS, int MINB, bool REALIGN>
 static void launch_s(double *a, long long sa, int *ipiv, double *b, long long sb, double *x, long long sx, int *info, int *redo, int ngroups, cudaStream_t s) {
@@ -594,6 +751,9 @@ int lu32p_launch(int variant, double *a, long long sa, int *ipiv, double *b, lon
       case 16: launch_s<2, MODE, 1, 12, false>(a, sa, ipiv, b, sb, x, sx, info, redo, ng, s); break;
       case 17: launch_s<1, MODE, 1, 16, false>(a, sa, ipiv, b, sb, x, sx, info, redo, ng, s); break;
       case 31: launch_q<MODE, 16, 1, true>(a, sa, ipiv, b, sb, x, sx, info, redo, ng, s); break;
+      case 40: launch_b<MODE, 1, 16>(a, sa, ipiv, b, sb, x, sx, info, redo, ng, s); break;
+      case 41: launch_b<MODE, 4, 4>(a, sa, ipiv, b, sb, x, sx, info, redo, ng, s); break;
+      case 42: launch_b<MODE, 1, 12>(a, sa, ipiv, b, sb, x, sx, info, redo, ng, s); break;
 #ifdef JB_LU32_ABLATIONS
 #define ABL1(v) case 100 + v: if (MODE == 1) launch_p<1, 1, 1, 16, false, v>(a, sa, ipiv, b, sb, x, sx, info, redo, ng, s); break; \
                 case 200 + v: if (MODE == 1) launch_p<2, 1, 1, 12, false, v>(a, sa, ipiv, b, sb, x, sx, info, redo, ng, s); break;

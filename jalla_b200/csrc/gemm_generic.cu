@@ -118,6 +118,7 @@ template <> struct FastPath<double> {
 template <> struct FastPath<float> {
   static int try_it(int ta, int tb, int m, int n, int k, float alpha, const float *A, int lda, const float *B, int ldb,
                     float beta, float *C, int ldc, cudaStream_t s, int tri) {
+    if (int took = sgemm_tma_try(ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, s, tri)) return took;
     return sgemm_simt_try(ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, s, tri);
   }
 };

@@ -189,6 +189,8 @@ int gemm_device(int ta, int tb, int m, int n, int k, T alpha, const T *A, int ld
 // fast paths return 1 when they took the call, 0 when the shape/alignment is not theirs
 int dgemm_dmma_try(int ta, int tb, int m, int n, int k, double alpha, const double *A, int lda,
                    const double *B, int ldb, double beta, double *C, int ldc, cudaStream_t s, int tri);
+int sgemm_tma_try(int ta, int tb, int m, int n, int k, float alpha, const float *A, int lda,
+                  const float *B, int ldb, float beta, float *C, int ldc, cudaStream_t s, int tri);
 int sgemm_simt_try(int ta, int tb, int m, int n, int k, float alpha, const float *A, int lda,
                    const float *B, int ldb, float beta, float *C, int ldc, cudaStream_t s, int tri);
 int zgemm_dmma_try(int ta, int tb, int m, int n, int k, cdouble alpha, const cdouble *A, int lda,

@@ -238,3 +238,17 @@ def test_host_pipelined_large(gpu, gpu_host, rng, ta, tb, beta):
         b = B[:k, j] if tb == 111 else B[j, :k]
         want = 1.25 * float(np.dot(a, b)) + (beta * C0[i, j] if beta else 0.0)
         assert abs(C1[i, j] - want) <= 1e-9 * k
+
+
+@pytest.mark.parametrize("t,ta,tb,order", [("d", 111, 111, 102), ("d", 112, 111, 102), ("d", 111, 112, 101),
+                                           ("z", 111, 113, 102), ("z", 112, 111, 101), ("s", 111, 111, 102), ("s", 112, 112, 101)])
+def test_headline_kernels_many_tiles_vs_openblas(gpu, blas, rng, t, ta, tb, order):
+    """The persistent tile loop of the tuned kernels at bench-like scale — more than 1000 C tiles per launch (several
+    tiles per CTA, band rasterisation wrapping, K = 4096 through every ring stage many times), both storage orders,
+    beta != 0 with a non-trivial alpha, padded leading dimensions — full matrix against OpenBLAS on the host with
+    north_star's Frobenius bound.  (The N = 16384 / 8192 configurations themselves are column-checked inside bench.py.)"""
+    m, n, k = (4224, 4352, 4096) if t in "ds" else (2944, 4224, 2048)      # 33 x 34 (d, s) / 46 x 33 (z) tiles
+    alpha, beta = (1.25, -0.75) if t in "ds" else (1.25 - 0.5j, -0.75 + 0.25j)
+    pad = (4, 8, 4) if t == "s" else (2, 4, 2)
+    Cg, Cr, A, B, *_ = run_both(gpu, blas, t, ta, tb, m, n, k, alpha, beta, rng, pad=pad, order=order)
+    assert_close(t, k, Cg, Cr, A, B)
