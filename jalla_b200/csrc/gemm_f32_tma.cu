@@ -11,7 +11,9 @@
 // and the thread's 8 rows (columns) are 2 x 4 consecutive ones in the first case, {t, t+16, ..., t+112} in the second, so
 // that every warp-wide load touches each bank group at most twice (the minimum for 256 bytes).  Either way a 4-k block
 // costs 16 vector loads for 256 FFMAs.  One elected thread per CTA issues the TMA loads into a 3-stage mbarrier ring,
-// two CTAs of 256 threads share an SM (persistent tile loop, band rasterisation for L2 reuse).
+// two CTAs of 256 threads share an SM (persistent tile loop, band rasterisation for L2 reuse).  Large products whose A is
+// MN-major (NoTrans — what Jalla's ## passes) run a 256 x 128 tile instead: 16 x 8 per thread, one CTA per SM with up to
+// 255 registers, 4 stages — 6 operand loads per 64 FFMA2 instead of 4 per 32.
 // Bound: FP32 FMA pipe, measured peak 72.35 TFLOP/s (tools/peaks.cu).
 #include "dmma_common.cuh"
 
@@ -19,10 +21,17 @@ namespace jb {
 namespace sgemm_tma {
 using dmma::smem_u32; using dmma::mbar_init; using dmma::mbar_expect_tx; using dmma::mbar_arrive; using dmma::mbar_wait; using dmma::tma_load_2d;
 
-constexpr int BM = 128, BN = 128, BK = 32, STAGES = 3, THREADS = 256, WARPS = THREADS / 32;
-constexpr int TILE_BYTES = BM * BK * 4, STAGE_BYTES = 2 * TILE_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 64;
+constexpr int BK = 32, THREADS = 256, WARPS = THREADS / 32;
 constexpr int GROUP_M = 16;
+// Tile shapes: a thread owns TM rows x TN columns of the 16*TM x 16*TN C tile.
+//   <8, 8>   128 x 128, 3 stages, two CTAs per SM (128 registers)                       — every operand layout
+//   <16, 8>  256 x 128, 4 stages, one CTA per SM (up to 255 registers), A MN-major only  — half the operand loads per FFMA2
+template <int TM, int TN> struct Shape {
+  static constexpr int BM = 16 * TM, BN = 16 * TN;
+  static constexpr int STAGES = (TM == 8 && TN == 8) ? 3 : 4, MINB = (TM == 8 && TN == 8) ? 2 : 1;
+  static constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 64;
+};
 
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
@@ -40,10 +49,13 @@ __device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f
 // index (row of A / column of B inside the tile) of a thread's e-th element, e = 0..7; t = its position 0..15
 template <bool MN> __device__ __forceinline__ int elem_idx(int t, int e) { return MN ? (e >> 2) * 64 + t * 4 + (e & 3) : t + 16 * e; }
 
-template <bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(THREADS, 2)
+template <bool A_MN, bool B_MN, int TM, int TN>
+__global__ void __launch_bounds__(THREADS, Shape<TM, TN>::MINB)
 sgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int m, int n, int k, float alpha,
                  float beta, float *__restrict__ C, int ldc, int tri) {
+  using SH = Shape<TM, TN>;
+  constexpr int BM = SH::BM, BN = SH::BN, STAGES = SH::STAGES, STAGE_BYTES = SH::STAGE_BYTES, TILE_BYTES = SH::A_BYTES;
+  static_assert(TM % 4 == 0 && TN % 4 == 0 && (A_MN || TM == 8) && (B_MN || TN == 8), "K-major operands are read 8 rows per thread");
   extern __shared__ unsigned char smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_full = base + STAGES * STAGE_BYTES, bar_empty = bar_full + STAGES * 8;
@@ -95,9 +107,9 @@ sgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     if (skipped(tm, tn)) continue;
     // accumulators as packed pairs: along the rows (acc2[ip][j] = rows 2ip, 2ip+1 of column j) unless only B is MN-major
     constexpr bool PACK_I = A_MN || !B_MN;
-    u64 acc2[32];
+    u64 acc2[TM * TN / 2];
 #pragma unroll
-    for (int i = 0; i < 32; i++) acc2[i] = 0ull;
+    for (int i = 0; i < TM * TN / 2; i++) acc2[i] = 0ull;
 
     for (int kt = 0; kt < KT; kt++) {
       if (tid == 0) issue_one();                       // keeps STAGES-1 loads in flight
@@ -117,43 +129,49 @@ sgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         }
 #pragma unroll
         for (int kk = 0; kk < 4; kk++) {
-          float a[8], b[8];
+          float a[TM], b[TN];
           if (A_MN) {
             const uint32_t row = sa + ((kb * 4 + kk) * BM + tx * 4) * 4;
-            const float4 a0 = lds128(row), a1 = lds128(row + 256);
-            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+#pragma unroll
+            for (int g = 0; g < TM / 4; g++) {
+              const float4 v = lds128(row + g * 256);
+              a[4 * g] = v.x; a[4 * g + 1] = v.y; a[4 * g + 2] = v.z; a[4 * g + 3] = v.w;
+            }
           } else {
 #pragma unroll
             for (int e = 0; e < 8; e++) a[e] = kk == 0 ? aq[e].x : (kk == 1 ? aq[e].y : (kk == 2 ? aq[e].z : aq[e].w));
           }
           if (B_MN) {
             const uint32_t row = sb + ((kb * 4 + kk) * BN + ty * 4) * 4;
-            const float4 b0 = lds128(row), b1 = lds128(row + 256);
-            b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+#pragma unroll
+            for (int g = 0; g < TN / 4; g++) {
+              const float4 v = lds128(row + g * 256);
+              b[4 * g] = v.x; b[4 * g + 1] = v.y; b[4 * g + 2] = v.z; b[4 * g + 3] = v.w;
+            }
           } else {
 #pragma unroll
             for (int e = 0; e < 8; e++) b[e] = kk == 0 ? bq[e].x : (kk == 1 ? bq[e].y : (kk == 2 ? bq[e].z : bq[e].w));
           }
           if (PACK_I) {
-            u64 ap[4], bd[8];
+            u64 ap[TM / 2], bd[TN];
 #pragma unroll
-            for (int p = 0; p < 4; p++) ap[p] = pack2(a[2 * p], a[2 * p + 1]);
+            for (int p = 0; p < TM / 2; p++) ap[p] = pack2(a[2 * p], a[2 * p + 1]);
 #pragma unroll
-            for (int j = 0; j < 8; j++) bd[j] = pack2(b[j], b[j]);
+            for (int j = 0; j < TN; j++) bd[j] = pack2(b[j], b[j]);
 #pragma unroll
-            for (int p = 0; p < 4; p++)
+            for (int p = 0; p < TM / 2; p++)
 #pragma unroll
-              for (int j = 0; j < 8; j++) acc2[p * 8 + j] = ffma2(ap[p], bd[j], acc2[p * 8 + j]);
+              for (int j = 0; j < TN; j++) acc2[p * TN + j] = ffma2(ap[p], bd[j], acc2[p * TN + j]);
           } else {
-            u64 ad[8], bp[4];
+            u64 ad[TM], bp[TN / 2];
 #pragma unroll
-            for (int i = 0; i < 8; i++) ad[i] = pack2(a[i], a[i]);
+            for (int i = 0; i < TM; i++) ad[i] = pack2(a[i], a[i]);
 #pragma unroll
-            for (int q = 0; q < 4; q++) bp[q] = pack2(b[2 * q], b[2 * q + 1]);
+            for (int q = 0; q < TN / 2; q++) bp[q] = pack2(b[2 * q], b[2 * q + 1]);
 #pragma unroll
-            for (int i = 0; i < 8; i++)
+            for (int i = 0; i < TM; i++)
 #pragma unroll
-              for (int q = 0; q < 4; q++) acc2[i * 4 + q] = ffma2(ad[i], bp[q], acc2[i * 4 + q]);
+              for (int q = 0; q < TN / 2; q++) acc2[i * (TN / 2) + q] = ffma2(ad[i], bp[q], acc2[i * (TN / 2) + q]);
           }
         }
       }
@@ -162,29 +180,28 @@ sgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
 
-    // epilogue: C = alpha*acc + beta*C
-    float acc[8][8];
-#pragma unroll
-    for (int u = 0; u < 8; u++)
-#pragma unroll
-      for (int v = 0; v < 4; v++) {
-        if (PACK_I) unpack2(acc2[v * 8 + u], acc[2 * v][u], acc[2 * v + 1][u]);      // u = column j, v = row pair
-        else unpack2(acc2[u * 4 + v], acc[u][2 * v], acc[u][2 * v + 1]);              // u = row i, v = column pair
-      }
+    // epilogue: C = alpha*acc + beta*C, one column of the micro-tile at a time
     const int row0 = tm * BM, col0 = tn * BN;
     const bool beta0 = (beta == 0.f);
     const bool vec_ok = A_MN && ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && tri == 0;
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
+    for (int j = 0; j < TN; j++) {
+      float acc[TM];
+#pragma unroll
+      for (int i = 0; i < TM; i++) {
+        float lo, hi;
+        if (PACK_I) { unpack2(acc2[(i >> 1) * TN + j], lo, hi); acc[i] = (i & 1) ? hi : lo; }
+        else { unpack2(acc2[i * (TN / 2) + (j >> 1)], lo, hi); acc[i] = (j & 1) ? hi : lo; }
+      }
       const int col = col0 + elem_idx<B_MN>(ty, j);
       if (col >= n) continue;
       float *ccol = C + (size_t)col * ldc;
       if (vec_ok) {
 #pragma unroll
-        for (int hh = 0; hh < 2; hh++) {
+        for (int hh = 0; hh < TM / 4; hh++) {
           const int r0 = row0 + hh * 64 + tx * 4;
           if (r0 >= m) continue;
-          float v[4] = {alpha * acc[hh * 4 + 0][j], alpha * acc[hh * 4 + 1][j], alpha * acc[hh * 4 + 2][j], alpha * acc[hh * 4 + 3][j]};
+          float v[4] = {alpha * acc[hh * 4 + 0], alpha * acc[hh * 4 + 1], alpha * acc[hh * 4 + 2], alpha * acc[hh * 4 + 3]};
           if (r0 + 3 < m) {
             if (!beta0) {
               const float4 c0 = *reinterpret_cast<const float4 *>(ccol + r0);
@@ -199,12 +216,12 @@ sgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
+        for (int i = 0; i < TM; i++) {
           const int row = row0 + elem_idx<A_MN>(tx, i);
           if (row >= m) continue;
           if (tri == 'L' && row < col) continue;
           if (tri == 'U' && row > col) continue;
-          const float v = alpha * acc[i][j];
+          const float v = alpha * acc[i];
           ccol[row] = beta0 ? v : fmaf(beta, ccol[row], v);
         }
       }
@@ -227,14 +244,15 @@ static int make_map_f32(CUtensorMap *map, const float *ptr, long dim0, long dim1
   return 0;
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int TM, int TN>
 static int launch(const CUtensorMap &ma, const CUtensorMap &mb, int m, int n, int k, float alpha, float beta, float *C, int ldc, int tri, cudaStream_t s) {
-  JB_ONCE_PER_DEVICE(JB_CUDA(cudaFuncSetAttribute(sgemm_tma_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)));
-  const int ntiles = ((m + BM - 1) / BM) * ((n + BN - 1) / BN);
-  int grid = std::min(ntiles, 2 * num_sms());
+  using SH = Shape<TM, TN>;
+  JB_ONCE_PER_DEVICE(JB_CUDA(cudaFuncSetAttribute(sgemm_tma_kernel<A_MN, B_MN, TM, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH::SMEM_BYTES)));
+  const int ntiles = ((m + SH::BM - 1) / SH::BM) * ((n + SH::BN - 1) / SH::BN);
+  int grid = std::min(ntiles, SH::MINB * num_sms());
   const int cap = option("gemm.max_ctas");
-  if (cap > 0 && 2 * cap < grid) grid = 2 * cap;
-  sgemm_tma_kernel<A_MN, B_MN><<<grid, THREADS, SMEM_BYTES, s>>>(ma, mb, m, n, k, alpha, beta, C, ldc, tri);
+  if (cap > 0 && SH::MINB * cap < grid) grid = SH::MINB * cap;
+  sgemm_tma_kernel<A_MN, B_MN, TM, TN><<<grid, THREADS, SH::SMEM_BYTES, s>>>(ma, mb, m, n, k, alpha, beta, C, ldc, tri);
   count_launch();
   JB_CUDA(cudaGetLastError());
   return 1;
@@ -245,21 +263,27 @@ int sgemm_tma_try(int ta, int tb, int m, int n, int k, float alpha, const float 
                   int ldc, cudaStream_t s, int tri) {
   using namespace sgemm_tma;
   if (m < 128 || n < 128 || k < 32) return 0;
-  if ((long)((m + BM - 1) / BM) * ((n + BN - 1) / BN) < 2 * 148) return 0;       // too few tiles to fill two CTAs per SM
+  if ((long)((m + 127) / 128) * ((n + 127) / 128) < 2 * 148) return 0;       // too few tiles to fill two CTAs per SM
   if (((uintptr_t)A & 15) || ((uintptr_t)B & 15) || (lda & 3) || (ldb & 3)) return 0;
   if (option("sgemm.simt") > 0) return 0;
   const bool a_mn = (ta == 111), b_mn = (tb != 111);
+  // the 256 x 128 tile (one CTA per SM) from 8 tiles per SM on, when A is MN-major (op(A) = A: what Jalla's ## passes)
+  const int want = option("sgemm.tile");       // 128 / 256 force a shape (tests, A/B timing); unset = by size
+  const bool big = a_mn && m >= 256 && want != 128 && (want == 256 || (long)((m + 255) / 256) * ((n + 127) / 128) >= 8 * 148);
+  const int bm = big ? 256 : 128;
   CUtensorMap ma, mb;
   int rc;
   // op(A) is m x k: NoTrans = stored m x k, m contiguous (MN-major); Trans = stored k x m, k contiguous (K-major)
-  if (a_mn) rc = make_map_f32(&ma, A, m, k, lda, BM, BK, false); else rc = make_map_f32(&ma, A, k, m, lda, BK, BM, true);
+  if (a_mn) rc = make_map_f32(&ma, A, m, k, lda, bm, BK, false); else rc = make_map_f32(&ma, A, k, m, lda, BK, 128, true);
   if (rc) return rc;
   // op(B) is k x n: NoTrans = stored k x n, k contiguous (K-major); Trans = stored n x k, n contiguous (MN-major)
-  if (b_mn) rc = make_map_f32(&mb, B, n, k, ldb, BN, BK, false); else rc = make_map_f32(&mb, B, k, n, ldb, BK, BN, true);
+  if (b_mn) rc = make_map_f32(&mb, B, n, k, ldb, 128, BK, false); else rc = make_map_f32(&mb, B, k, n, ldb, BK, 128, true);
   if (rc) return rc;
-  if (a_mn && b_mn) return launch<true, true>(ma, mb, m, n, k, alpha, beta, C, ldc, tri, s);
-  if (a_mn && !b_mn) return launch<true, false>(ma, mb, m, n, k, alpha, beta, C, ldc, tri, s);
-  if (!a_mn && b_mn) return launch<false, true>(ma, mb, m, n, k, alpha, beta, C, ldc, tri, s);
-  return launch<false, false>(ma, mb, m, n, k, alpha, beta, C, ldc, tri, s);
+  if (big && b_mn) return launch<true, true, 16, 8>(ma, mb, m, n, k, alpha, beta, C, ldc, tri, s);
+  if (big) return launch<true, false, 16, 8>(ma, mb, m, n, k, alpha, beta, C, ldc, tri, s);
+  if (a_mn && b_mn) return launch<true, true, 8, 8>(ma, mb, m, n, k, alpha, beta, C, ldc, tri, s);
+  if (a_mn && !b_mn) return launch<true, false, 8, 8>(ma, mb, m, n, k, alpha, beta, C, ldc, tri, s);
+  if (!a_mn && b_mn) return launch<false, true, 8, 8>(ma, mb, m, n, k, alpha, beta, C, ldc, tri, s);
+  return launch<false, false, 8, 8>(ma, mb, m, n, k, alpha, beta, C, ldc, tri, s);
 }
 }  // namespace jb

@@ -252,3 +252,18 @@ def test_headline_kernels_many_tiles_vs_openblas(gpu, blas, rng, t, ta, tb, orde
     pad = (4, 8, 4) if t == "s" else (2, 4, 2)
     Cg, Cr, A, B, *_ = run_both(gpu, blas, t, ta, tb, m, n, k, alpha, beta, rng, pad=pad, order=order)
     assert_close(t, k, Cg, Cr, A, B)
+
+
+@pytest.mark.parametrize("ta,tb,order,m,n,k", [(111, 111, 102, 2304, 1408, 1000), (111, 112, 102, 2560, 1536, 520),
+                                               (111, 111, 101, 1408, 2304, 776), (111, 111, 102, 9216, 4480, 264)])
+def test_sgemm_256x128_tile_vs_openblas(gpu, blas, rng, ta, tb, order, m, n, k):
+    """The 256 x 128 tile of the TMA-staged sgemm (A MN-major; forced by sgemm.tile = 256 below its size threshold, taken by
+    size in the last case): ragged M, N and K edges, padded leading dimensions, alpha and beta != 0, a row-major caller
+    (order 101 keeps the transpose flags and swaps the operands, so the 256-row side is then n)."""
+    from jalla_b200._lib import lib
+    lib.jb_set_option(b"sgemm.tile", 256 if m < 9000 else -1)
+    try:
+        Cg, Cr, A, B, *_ = run_both(gpu, blas, "s", ta, tb, m, n, k, 1.25, -0.75, rng, pad=(4, 8, 4), order=order)
+    finally:
+        lib.jb_set_option(b"sgemm.tile", -1)
+    assert_close("s", k, Cg, Cr, A, B)
