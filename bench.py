@@ -485,7 +485,8 @@ def main():
         if lu is not None:
             del lu
         torch.cuda.empty_cache()
-        for t, n, peak, bound in (("z", 8192, DMMA_PEAK_TFLOPS, "FP64 DMMA"), ("s", 16384, FFMA_PEAK_TFLOPS, "FP32 FFMA (no TF32)")):
+        for t, n, peak, bound in (("z", 8192, DMMA_PEAK_TFLOPS, "FP64 DMMA"), ("s", 16384, FFMA_PEAK_TFLOPS, "FP32 FFMA (no TF32)"),
+                                  ("c", 8192, FFMA_PEAK_TFLOPS, "FP32 FFMA, 4M complex (no TF32)")):
             g2 = jdist.ShardedGemm(grid, n, seed=SEED, t=t)
             for _ in range(2):
                 g2.step()

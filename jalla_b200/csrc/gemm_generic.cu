@@ -122,6 +122,12 @@ template <> struct FastPath<float> {
     return sgemm_simt_try(ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, s, tri);
   }
 };
+template <> struct FastPath<cfloat> {
+  static int try_it(int ta, int tb, int m, int n, int k, cfloat alpha, const cfloat *A, int lda, const cfloat *B, int ldb,
+                    cfloat beta, cfloat *C, int ldc, cudaStream_t s, int tri) {
+    return cgemm_tma_try(ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, s, tri);
+  }
+};
 template <> struct FastPath<cdouble> {
   static int try_it(int ta, int tb, int m, int n, int k, cdouble alpha, const cdouble *A, int lda, const cdouble *B, int ldb,
                     cdouble beta, cdouble *C, int ldc, cudaStream_t s, int tri) {

@@ -193,6 +193,8 @@ int sgemm_tma_try(int ta, int tb, int m, int n, int k, float alpha, const float 
                   const float *B, int ldb, float beta, float *C, int ldc, cudaStream_t s, int tri);
 int sgemm_simt_try(int ta, int tb, int m, int n, int k, float alpha, const float *A, int lda,
                    const float *B, int ldb, float beta, float *C, int ldc, cudaStream_t s, int tri);
+int cgemm_tma_try(int ta, int tb, int m, int n, int k, cfloat alpha, const cfloat *A, int lda,
+                  const cfloat *B, int ldb, cfloat beta, cfloat *C, int ldc, cudaStream_t s, int tri);
 int zgemm_dmma_try(int ta, int tb, int m, int n, int k, cdouble alpha, const cdouble *A, int lda,
                    const cdouble *B, int ldb, cdouble beta, cdouble *C, int ldc, cudaStream_t s, int tri);
 

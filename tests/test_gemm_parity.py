@@ -241,7 +241,8 @@ def test_host_pipelined_large(gpu, gpu_host, rng, ta, tb, beta):
 
 
 @pytest.mark.parametrize("t,ta,tb,order", [("d", 111, 111, 102), ("d", 112, 111, 102), ("d", 111, 112, 101),
-                                           ("z", 111, 113, 102), ("z", 112, 111, 101), ("s", 111, 111, 102), ("s", 112, 112, 101)])
+                                           ("z", 111, 113, 102), ("z", 112, 111, 101), ("s", 111, 111, 102), ("s", 112, 112, 101),
+                                           ("c", 111, 111, 102), ("c", 113, 112, 102), ("c", 112, 113, 101)])
 def test_headline_kernels_many_tiles_vs_openblas(gpu, blas, rng, t, ta, tb, order):
     """The persistent tile loop of the tuned kernels at bench-like scale — more than 1000 C tiles per launch (several
     tiles per CTA, band rasterisation wrapping, K = 4096 through every ring stage many times), both storage orders,
@@ -267,3 +268,14 @@ def test_sgemm_256x128_tile_vs_openblas(gpu, blas, rng, ta, tb, order, m, n, k):
     finally:
         lib.jb_set_option(b"sgemm.tile", -1)
     assert_close("s", k, Cg, Cr, A, B)
+
+
+@pytest.mark.parametrize("ta,tb", list(itertools.product((111, 112, 113), (111, 112, 113))))
+def test_cgemm_tma_all_ops_ragged(gpu, blas, rng, force_dmma, ta, tb):
+    """The TMA-staged FFMA2 cgemm (128 x 128 complex tile) for every op(A), op(B) pair: ragged M, N and K edges (TMA zero
+    fill, predicated stores), even padded leading dimensions, complex alpha and beta."""
+    m, n, k = 300, 282, 203
+    Cg, Cr, A, B, *_ = run_both(gpu, blas, "c", ta, tb, m, n, k, 0.75 - 0.5j, -1.25 + 0.25j, rng, pad=(2, 4, 6))
+    assert_close("c", k, Cg, Cr, A, B)
+    Cg, Cr, A, B, *_ = run_both(gpu, blas, "c", ta, tb, m, n, k, 1.0, 0.0, rng, pad=(0, 0, 0), order=101)
+    assert_close("c", k, Cg, Cr, A, B)
