@@ -74,6 +74,41 @@ inline int make_map_f64(CUtensorMap *map, const void *ptr, long rows, long cols,
   return 0;
 }
 
+
+// Tile sequence of one CTA of a persistent GEMM: band rasterisation (GROUP_M tile rows per band, column-major inside a band,
+// for L2 reuse), CTA c takes entries c, c + grid, c + 2 grid, ... of the sequence.  In triangle mode (tri = 'L' / 'U': only
+// tiles that touch that triangle are computed — Cholesky trailing updates, syrk / herk) the sequence holds ONLY the kept
+// tiles, so every CTA gets the same number of them (+-1); striding over all tiles and skipping left the CTAs of a
+// 52-wave update with 49..55 tiles each.  The walker advances a (band, tile column) cursor monotonically, O(columns) per
+// CTA and launch in total.  Square tiles (BM == BN) assumed for the triangle test.
+template <int GROUP_M>
+struct TileWalker {
+  int tiles_m, tiles_n, tri;
+  int band = 0, tn = 0, base = 0;       // cursor: kept tiles before column tn of this band
+  __device__ TileWalker(int tm_, int tn_, int tri_) : tiles_m(tm_), tiles_n(tn_), tri(tri_) {}
+  // coordinates of the idx-th tile of the sequence (idx must not decrease between calls); false when past the end
+  __device__ __forceinline__ bool at(int idx, int &tm_out, int &tn_out) {
+    if (tri == 0) {
+      if (idx >= tiles_m * tiles_n) return false;
+      const int per_band = GROUP_M * tiles_n, b = idx / per_band, in_band = idx % per_band;
+      const int first_m = b * GROUP_M, gsz = min(tiles_m - first_m, GROUP_M);
+      tm_out = first_m + in_band % gsz; tn_out = in_band / gsz;
+      return true;
+    }
+    while (band * GROUP_M < tiles_m) {
+      const int first_m = band * GROUP_M, end_m = min(tiles_m, first_m + GROUP_M);
+      // rows of column tn in this band that touch the triangle: 'L' tm >= tn, 'U' tm <= tn
+      const int lo = tri == 'L' ? max(first_m, tn) : first_m;
+      const int hi = tri == 'L' ? end_m : min(end_m, tn + 1);
+      const int cnt = max(hi - lo, 0);
+      if (idx < base + cnt) { tm_out = lo + (idx - base); tn_out = tn; return true; }
+      base += cnt;
+      if (++tn == tiles_n) { tn = 0; ++band; }
+    }
+    return false;
+  }
+};
+
 }  // namespace dmma
 // Asynchronous L2 prefetch of `bytes` (multiple of 16) at a 16-byte aligned global address.
 __device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes) {

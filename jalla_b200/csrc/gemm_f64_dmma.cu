@@ -47,19 +47,7 @@ template <bool KM> __device__ __forceinline__ uint32_t frag_off(int j, int s, in
   return (uint32_t)((j >> 1) * 2048 + kap * 128 + ((((i15 >> 1) ^ (kap & 7)) & 7) << 4) + (i15 & 1) * 8);
 }
 
-__device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int &tm, int &tn) {
-  const int per_band = GROUP_M * tiles_n;
-  const int band = tile / per_band, in_band = tile % per_band;
-  const int first_m = band * GROUP_M;
-  const int gsz = min(tiles_m - first_m, GROUP_M);
-  tm = first_m + in_band % gsz;
-  tn = in_band / gsz;
-}
-__device__ __forceinline__ bool tile_skipped(int tri, int tm, int tn) {
-  if (tri == 'L') return tm * BM + BM - 1 < tn * BN;
-  if (tri == 'U') return tn * BN + BN - 1 < tm * BM;
-  return false;
-}
+static_assert(BM == BN, "TileWalker's triangle test assumes square tiles");
 
 template <bool A_KM, bool B_KM>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -71,7 +59,6 @@ dgemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   const uint32_t bar_empty = bar_full + STAGES * 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (m + BM - 1) / BM, tiles_n = (n + BN - 1) / BN;
-  const int ntiles = tiles_m * tiles_n;
   const int KT = (k + BK - 1) / BK;
 
   if (threadIdx.x == 0) {
@@ -94,9 +81,9 @@ dgemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       // tile's C columns over the main loop instead, so the epilogue reads hit L2.
       const bool pf = beta != 0.0 && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && ((ldc & 1) == 0);
       const int pf_step = (BN + KT - 1) / KT;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        int tm, tn; tile_coords(tile, tiles_m, tiles_n, tm, tn);
-        if (tile_skipped(tri, tm, tn)) continue;
+      TileWalker<GROUP_M> walk(tiles_m, tiles_n, tri);
+      int tm, tn;
+      for (int tile = blockIdx.x; walk.at(tile, tm, tn); tile += gridDim.x) {
         int pf_col = 0;
         const int pf_cols = min(BN, n - tn * BN);
         const uint32_t pf_bytes = (uint32_t)(min(BM, m - tm * BM) * 8) & ~15u;
@@ -142,9 +129,9 @@ dgemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   int stage = 0; uint32_t phase = 0;
   const bool beta0 = (beta == 0.0);
 
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    int tm, tn; tile_coords(tile, tiles_m, tiles_n, tm, tn);
-    if (tile_skipped(tri, tm, tn)) continue;
+  TileWalker<GROUP_M> walk(tiles_m, tiles_n, tri);
+  int tm, tn;
+  for (int tile = blockIdx.x; walk.at(tile, tm, tn); tile += gridDim.x) {
     double acc[8][4][2];
 #pragma unroll
     for (int i = 0; i < 8; i++)

@@ -211,5 +211,9 @@ template <typename T> int potrf_device(char uplo, int n, T *A, int lda, int *d_i
 template <typename T> int potrs_device(char uplo, int n, int nrhs, const T *A, int lda, T *B, int ldb, cudaStream_t s);
 // side 141 left / 142 right, uplo 121 upper / 122 lower, trans 111/112/113, diag 131 non-unit / 132 unit
 template <typename T> int trsm_device(int side, int uplo, int trans, int diag, int m, int n, T alpha, const T *A, int lda, T *B, int ldb, cudaStream_t s);
+// the same solve as two GEMMs per 64 rows of the triangle (inverted diagonal blocks; trsm_inv.cu), alpha == 1
+template <typename T> int trsm_inv_device(int side, int stored_lower, int trans, int unit, int m, int n, const T *A, int lda, T *B, int ldb, cudaStream_t s);
+// wide enough for the GEMM form to pay (order of the triangle, number of right-hand sides / rows)
+inline bool trsm_inv_pays(int nt, int other) { return nt >= 128 && other >= 256 && option("trsm.inv") != 0; }
 
 }  // namespace jb

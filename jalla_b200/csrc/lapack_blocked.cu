@@ -1183,6 +1183,7 @@ int getrf_device(int m, int n, T *A, int lda, int *d_ipiv, int *d_info, cudaStre
 template <typename T>
 static int trsm_left_blocked(int stored_lower, int trans, int unit, int n, int nrhs, const T *A, int lda, T *B, int ldb,
                              cudaStream_t s) {
+  if (trsm_inv_pays(n, nrhs)) return trsm_inv_device<T>(141, stored_lower, trans, unit, n, nrhs, A, lda, B, ldb, s);
   const int eff_lower = (trans == 111) ? stored_lower : !stored_lower;
   const int nblk = (n + NB - 1) / NB;
   int blocks = (nrhs + 7) / 8; if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
@@ -1429,8 +1430,8 @@ static int potrf_panels(char uplo, int n, T *A, int lda, int *d_info, int NB2, c
   struct CountFree { int *p; cudaStream_t st; ~CountFree() { ws_free(p, st); } } count_free{d_count, s};
   JB_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), s));
   // C[r0:, c0:c1] -= L[r0:, k0:k1] * L[c0:c1, k0:k1]^H in lower form (rows >= columns only), or its mirror image
-  auto update = [&](int r0, int c0, int c1, int k0, int k1, cudaStream_t st) -> int {
-    const int mr = n - r0, nc = c1 - c0, kk = k1 - k0;
+  auto update = [&](int r0, int c0, int c1, int k0, int k1, cudaStream_t st, int r_end = -1) -> int {
+    const int mr = (r_end < 0 ? n : r_end) - r0, nc = c1 - c0, kk = k1 - k0;
     if (mr <= 0 || nc <= 0) return 0;
     if (lower)
       return gemm_device<T>(111, tc, mr, nc, kk, minus1, A + r0 + (size_t)k0 * lda, lda, A + c0 + (size_t)k0 * lda, lda, one,
@@ -1439,17 +1440,29 @@ static int potrf_panels(char uplo, int n, T *A, int lda, int *d_info, int NB2, c
                           A + c0 + (size_t)r0 * lda, lda, st, 'U');
   };
   // the 32-column panels of outer block [J0, J0 + jb2) with the updates that stay inside the block
-  auto factor_block = [&](int J0, int jb2, cudaStream_t st) -> int {
+  // split = true: only the rows of the diagonal block (a few CTAs); the rows below follow as ONE triangular solve in
+  // GEMM form (trsm_inv.cu) — the block column below a 512-wide outer block is then 17 launches on the tuned GEMM instead
+  // of 16 x (panel over all rows + skinny rank-32 update), and the look-ahead chain needs 8 free SMs instead of 16-64.
+  auto factor_block = [&](int J0, int jb2, cudaStream_t st, bool split) -> int {
+    const int r_end = split ? J0 + jb2 : n;
     for (int j0 = J0; j0 < J0 + jb2; j0 += NB) {
       const int jb = (J0 + jb2 - j0 < NB) ? (J0 + jb2 - j0) : NB;
-      const int m = n - j0;
+      const int m = r_end - j0;
       const int G = m > NB ? (m - NB + (CHOL_PANEL_THREADS - NB) - 1) / (CHOL_PANEL_THREADS - NB) : 1;
       chol_panel_kernel<T><<<G, CHOL_PANEL_THREADS, shm, st>>>(lower, m, jb, A + j0 + (size_t)j0 * lda, lda, d_info, j0, d_count);
       count_launch();
-      if (int rc = update(j0 + jb, j0 + jb, J0 + jb2, j0, j0 + jb, st)) return rc;
+      if (int rc = update(j0 + jb, j0 + jb, J0 + jb2, j0, j0 + jb, st, r_end)) return rc;
     }
     return 0;
   };
+  auto solve_below = [&](int J0, int jb2, cudaStream_t st) -> int {
+    const int rem = n - J0 - jb2;
+    if (rem <= 0) return 0;
+    T *Ajj = A + J0 + (size_t)J0 * lda;
+    if (lower) return trsm_inv_device<T>(142, 1, tc, 0, rem, jb2, Ajj, lda, A + (J0 + jb2) + (size_t)J0 * lda, lda, st);   // A21 <- A21 L11^{-H}
+    return trsm_inv_device<T>(141, 0, tc, 0, jb2, rem, Ajj, lda, A + J0 + (size_t)(J0 + jb2) * lda, lda, st);              // A12 <- U11^{-H} A12
+  };
+  const bool split = option("potrf.split") > 0 && NB2 >= 128;      // measured (tools/time_potrf_rsv.py): 16384: 64.4 vs 65.4 ms, 8192: 15.1 vs 13.2 — off by default
   // Look-ahead as in getrf_device: the trailing update is split into the next block's columns and the rest, and the
   // next block is factorised on a second, higher-priority stream while the main stream finishes the rest.  The panel
   // CTAs are independent (no co-residency needed), so a fixed 16 SMs are kept free of the persistent DMMA GEMM.
@@ -1462,8 +1475,9 @@ static int potrf_panels(char uplo, int n, T *A, int lda, int *d_info, int NB2, c
   bool factored = false;
   for (int J0 = 0; J0 < n && !rc; J0 += NB2) {
     const int jb2 = (n - J0 < NB2) ? (n - J0) : NB2;
-    if (!factored) rc = factor_block(J0, jb2, s);
+    if (!factored) rc = factor_block(J0, jb2, s, split);
     factored = false;
+    if (!rc && split) rc = solve_below(J0, jb2, s);
     if (rc) break;
     const int c0 = J0 + jb2;
     if (c0 >= n) break;
@@ -1473,11 +1487,28 @@ static int potrf_panels(char uplo, int n, T *A, int lda, int *d_info, int NB2, c
       if (rc) break;
       JB_CUDA(cudaEventRecord(ev_first, s));
       JB_CUDA(cudaStreamWaitEvent(s2, ev_first, 0));
-      rc = factor_block(c0, jn, s2);
+      rc = factor_block(c0, jn, s2, split);
       if (rc) break;
       JB_CUDA(cudaEventRecord(ev_panel, s2));
       {
-        GemmCapScope cap(num_sms() - 16);
+        // SMs kept free of the persistent GEMM for the panel chain of the next block.  Unsplit, the chain runs its G
+        // independent panel CTAs in waves over the free SMs, so it is as long as the update when few SMs face a tall panel,
+        // and the update is longer than it has to be when many SMs wait for a short one: pick the split that balances the
+        // two (model: update at ~0.18 TFLOP/s per SM, a panel wave 21 us, 35 us per 32-column step for the skinny update).
+        int rsv = option("potrf.reserve_sms");
+        if (rsv < 0 && split) rsv = 8;
+        if (rsv < 0) {
+          const double mt = (double)(n - c0 - jn), up_flop = mt * mt * jb2 * (Num<T>::cplx ? 4.0 : 1.0);
+          const int G = (n - c0 - NB + (CHOL_PANEL_THREADS - NB) - 1) / (CHOL_PANEL_THREADS - NB);
+          double best = 1e30;
+          for (int r : {8, 16, 24, 32, 48, 64}) {
+            const double t_up = up_flop / (0.182e6 * (num_sms() - r));
+            const double t_chain = (jn / (double)NB) * (((G + r - 1) / r) * 21.0 + 35.0);
+            const double t = t_up > t_chain ? t_up : t_chain;
+            if (t < best) { best = t; rsv = r; }
+          }
+        }
+        GemmCapScope cap(rsv > 0 ? num_sms() - rsv : 0);
         rc = update(c0 + jn, c0 + jn, n, J0, c0, s);
       }
       JB_CUDA(cudaStreamWaitEvent(s, ev_panel, 0));
@@ -1601,6 +1632,7 @@ int trsm_device(int side, int uplo, int trans, int diag, int m, int n, T alpha, 
   // Right side: X op(A) = B.  Column-block sweep: effective-upper op(A) runs left to right, effective-lower
   // right to left; each step solves a 32-wide column block against the diagonal block (one thread per row of
   // B) and updates the remaining columns with one GEMM.
+  if (trsm_inv_pays(n, m)) return trsm_inv_device<T>(142, stored_lower, trans, unit, m, n, A, lda, B, ldb, s);
   const int eff_upper = (trans == 111) ? !stored_lower : stored_lower;
   const int nblk = (n + NB - 1) / NB;
   const T minus1 = Num<T>::neg(Num<T>::one()), one = Num<T>::one();

@@ -1,0 +1,162 @@
+// Triangular solves with many right-hand sides as GEMMs: B <- op(A)^{-1} B (Left) or B op(A)^{-1} (Right), column-major —
+// the level-3 step inside the blocked factorisations (the unit-lower block-row solve of ?getrf, the panel solve of ?potrf,
+// ?getrs / ?potrs / ?getri with wide right-hand sides) and behind cblas_?trsm
+// (/root/reference/Numeric/Jalla/Foreign/BlasOps.hs:57, Foreign/LAPACKE.chs:697-706,741-744).
+//
+// The 32-wide substitution kernels of lapack_blocked.cu pay two launch-bound kernels per 32 rows of the triangle
+// (ncu, dgetrf 16384: 976 trsm_small launches + their rank-32 updates = 1 ms of every 3.3 ms outer step).  Here the 64 x 64
+// diagonal blocks of the triangle are inverted once (one CTA per block, forward substitution on the identity in shared
+// memory) and the sweep becomes two GEMMs per 64 rows on the tuned kernels:
+//     X_c = op(inv(A_cc)) B_c            B_rest -= op(A)_{rest,c} X_c            (Left; Right mirrors it)
+// X is collected in a scratch copy (a GEMM cannot run in place) and copied back once at the end.  Inverting only the small
+// diagonal blocks keeps the error of plain blocked substitution up to the conditioning of a 64 x 64 block.
+#include "jb_common.cuh"
+
+namespace jb {
+
+constexpr int NBI = 64, NBI_LD = NBI + 1;
+
+// Dinv[b] (NBI x NBI, ld NBI, storage orientation, other triangle zero) = inverse of the b-th diagonal block of the
+// triangular matrix A (order nt); a ragged last block is padded with the identity.
+template <typename T>
+__global__ void __launch_bounds__(256) trtri_diag_kernel(int stored_lower, int unit, int nt, const T *__restrict__ A, int lda, T *__restrict__ Dinv) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T *D = reinterpret_cast<T *>(smem_raw);          // effective lower block L (= A_bb or its transpose), row-major, padded
+  T *X = D + NBI * NBI_LD;                          // inv(L)
+  const int b = blockIdx.x, r0 = b * NBI, nb = min(NBI, nt - r0), tid = threadIdx.x;
+  for (int idx = tid; idx < NBI * NBI; idx += blockDim.x) {
+    const int i = idx % NBI, j = idx / NBI;         // storage element (i, j) of the block
+    const int li = stored_lower ? i : j, lk = stored_lower ? j : i;
+    if (li < lk) continue;
+    T v = (li == lk) ? Num<T>::one() : Num<T>::zero();
+    if (i < nb && j < nb && !(unit && li == lk)) v = A[(size_t)(r0 + i) + (size_t)(r0 + j) * lda];
+    D[li * NBI_LD + lk] = v;
+  }
+  __syncthreads();
+  if (tid < NBI) {
+    // column j of inv(L): forward substitution of L x = e_j, every thread in lockstep over the rows (x_k = 0 above j)
+    const int j = tid;
+    for (int i = 0; i < NBI; i++) {
+      T acc0 = (i == j) ? Num<T>::one() : Num<T>::zero(), acc1 = Num<T>::zero();
+      int k = 0;
+      for (; k + 1 < i; k += 2) {
+        acc0 = Num<T>::sub(acc0, Num<T>::mul(D[i * NBI_LD + k], X[k * NBI_LD + j]));
+        acc1 = Num<T>::sub(acc1, Num<T>::mul(D[i * NBI_LD + k + 1], X[(k + 1) * NBI_LD + j]));
+      }
+      if (k < i) acc0 = Num<T>::sub(acc0, Num<T>::mul(D[i * NBI_LD + k], X[k * NBI_LD + j]));
+      T x = Num<T>::add(acc0, acc1);
+      if (i < j) x = Num<T>::zero();
+      else if (!unit) x = Num<T>::mul(x, Num<T>::recip(D[i * NBI_LD + i]));
+      X[i * NBI_LD + j] = x;
+    }
+  }
+  __syncthreads();
+  T *out = Dinv + (size_t)b * NBI * NBI;
+  for (int idx = tid; idx < NBI * NBI; idx += blockDim.x) {
+    const int i = idx % NBI, j = idx / NBI;
+    const int li = stored_lower ? i : j, lk = stored_lower ? j : i;
+    out[idx] = (li >= lk) ? X[li * NBI_LD + lk] : Num<T>::zero();      // inv(U) = inv(U^T)^T
+  }
+}
+
+// Triangles of order <= REC_BASE: the 64-row sweep.
+template <typename T>
+static int trsm_inv_base(int side, int stored_lower, int trans, int unit, int m, int n, const T *A, int lda, T *B, int ldb, cudaStream_t s) {
+  const int nt = side == 141 ? m : n, nblk = (nt + NBI - 1) / NBI;
+  const T minus1 = Num<T>::neg(Num<T>::one()), one = Num<T>::one(), zero = Num<T>::zero();
+  T *Dinv = nullptr, *W = nullptr;
+  if (int rc = ws_alloc((void **)&Dinv, sizeof(T) * (size_t)nblk * NBI * NBI, s)) return rc;
+  const int ldw = m + (m & 1);
+  if (int rc = ws_alloc((void **)&W, sizeof(T) * (size_t)ldw * n, s)) { ws_free(Dinv, s); return rc; }
+  const int shm = 2 * NBI * NBI_LD * (int)sizeof(T);
+  int rc = 0;
+  {
+    static_assert(2 * NBI * NBI_LD * 16 <= 200 * 1024, "shared memory of the block inversion");
+    cudaError_t e = cudaSuccess;
+    if (shm > 48 * 1024) e = cudaFuncSetAttribute(trtri_diag_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, shm);
+    if (e == cudaSuccess) {
+      trtri_diag_kernel<T><<<nblk, 256, shm, s>>>(stored_lower, unit, nt, A, lda, Dinv);
+      count_launch();
+      e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) { set_error(JB_ERR_CUDA, "trtri_diag launch failed: %s", cudaGetErrorString(e)); rc = JB_ERR_CUDA; }
+  }
+  const int eff_lower = (trans == 111) ? stored_lower : !stored_lower;      // shape of op(A)
+  // Left: op(A) lower runs top-down, upper bottom-up.  Right: X op(A) = B with op(A) upper runs left to right.
+  const bool ascending = (side == 141) ? eff_lower : !eff_lower;
+  for (int bi = 0; bi < nblk && !rc; bi++) {
+    const int c = ascending ? bi : nblk - 1 - bi;
+    const int p0 = c * NBI, pb = min(NBI, nt - p0);
+    const int rest0 = ascending ? p0 + pb : 0, cnt = ascending ? nt - p0 - pb : p0;
+    const T *Dc = Dinv + (size_t)c * NBI * NBI;
+    if (side == 141) {
+      rc = gemm_device<T>(trans, 111, pb, n, pb, one, Dc, NBI, B + p0, ldb, zero, W + p0, ldw, s, 0);
+      if (!rc && cnt > 0) {
+        // op(A)[rest, c]: stored block A[rest, c] (NoTrans) or op of the stored block A[c, rest]
+        const T *Ab = (trans == 111) ? A + rest0 + (size_t)p0 * lda : A + p0 + (size_t)rest0 * lda;
+        rc = gemm_device<T>(trans, 111, cnt, n, pb, minus1, Ab, lda, W + p0, ldw, one, B + rest0, ldb, s, 0);
+      }
+    } else {
+      rc = gemm_device<T>(111, trans, m, pb, pb, one, B + (size_t)p0 * ldb, ldb, Dc, NBI, zero, W + (size_t)p0 * ldw, ldw, s, 0);
+      if (!rc && cnt > 0) {
+        // op(A)[c, rest]: stored block A[c, rest] (NoTrans) or op of the stored block A[rest, c]
+        const T *Ab = (trans == 111) ? A + p0 + (size_t)rest0 * lda : A + rest0 + (size_t)p0 * lda;
+        rc = gemm_device<T>(111, trans, m, cnt, pb, minus1, W + (size_t)p0 * ldw, ldw, Ab, lda, one, B + (size_t)rest0 * ldb, ldb, s, 0);
+      }
+    }
+  }
+  if (!rc) rc = lacpy_device<T>(111, m, n, W, ldw, B, ldb, s);
+  ws_free(W, s);
+  ws_free(Dinv, s);
+  return rc;
+}
+
+// side 141 Left / 142 Right; A is the stored triangle (order m for Left, n for Right); alpha already applied by the caller.
+// Larger triangles are halved recursively — solve one half, update the other with ONE GEMM whose inner dimension is the
+// half (the efficient shape for the tuned kernels), solve the other half — down to REC_BASE, where the 64-row sweep runs
+// (dtrsm n = nrhs = 8192: 63.6 ms with the 32-row kernels, 36.3 ms with the sweep alone).
+constexpr int REC_BASE = 512;
+template <typename T>
+int trsm_inv_device(int side, int stored_lower, int trans, int unit, int m, int n, const T *A, int lda, T *B, int ldb, cudaStream_t s) {
+  if (m <= 0 || n <= 0) return 0;
+  if (!Num<T>::cplx && trans == 113) trans = 112;
+  const int nt = side == 141 ? m : n;
+  // narrow right-hand sides leave the coupling GEMM too few tiles (n = 8192, nrhs = 512: 6.2 ms halved, 5.0 ms swept)
+  if (nt <= REC_BASE || (side == 141 ? n : m) < 1024) return trsm_inv_base<T>(side, stored_lower, trans, unit, m, n, A, lda, B, ldb, s);
+  const int h = ((nt / 2 + NBI - 1) / NBI) * NBI, r = nt - h;
+  const T minus1 = Num<T>::neg(Num<T>::one()), one = Num<T>::one();
+  const int eff_lower = (trans == 111) ? stored_lower : !stored_lower;
+  const bool ascending = (side == 141) ? eff_lower : !eff_lower;
+  const T *A11 = A, *A22 = A + h + (size_t)h * lda;
+  // the off-diagonal block of op(A) that couples the halves: stored below the diagonal (A + h) or right of it (A + h*lda)
+  const T *Aoff = (stored_lower ? A + h : A + (size_t)h * lda);
+  int rc;
+  if (side == 141) {
+    T *B1 = B, *B2 = B + h;
+    if (ascending) {            // op(A) lower: X1, then B2 -= op(A)[h:, :h] X1, then X2
+      if ((rc = trsm_inv_device<T>(side, stored_lower, trans, unit, h, n, A11, lda, B1, ldb, s))) return rc;
+      if ((rc = gemm_device<T>(trans, 111, r, n, h, minus1, Aoff, lda, B1, ldb, one, B2, ldb, s, 0))) return rc;
+      return trsm_inv_device<T>(side, stored_lower, trans, unit, r, n, A22, lda, B2, ldb, s);
+    }
+    if ((rc = trsm_inv_device<T>(side, stored_lower, trans, unit, r, n, A22, lda, B2, ldb, s))) return rc;
+    if ((rc = gemm_device<T>(trans, 111, h, n, r, minus1, Aoff, lda, B2, ldb, one, B1, ldb, s, 0))) return rc;
+    return trsm_inv_device<T>(side, stored_lower, trans, unit, h, n, A11, lda, B1, ldb, s);
+  }
+  T *B1 = B, *B2 = B + (size_t)h * ldb;
+  if (ascending) {              // op(A) upper: X1, then B2 -= X1 op(A)[:h, h:], then X2
+    if ((rc = trsm_inv_device<T>(side, stored_lower, trans, unit, m, h, A11, lda, B1, ldb, s))) return rc;
+    if ((rc = gemm_device<T>(111, trans, m, r, h, minus1, B1, ldb, Aoff, lda, one, B2, ldb, s, 0))) return rc;
+    return trsm_inv_device<T>(side, stored_lower, trans, unit, m, r, A22, lda, B2, ldb, s);
+  }
+  if ((rc = trsm_inv_device<T>(side, stored_lower, trans, unit, m, r, A22, lda, B2, ldb, s))) return rc;
+  if ((rc = gemm_device<T>(111, trans, m, h, r, minus1, B2, ldb, Aoff, lda, one, B1, ldb, s, 0))) return rc;
+  return trsm_inv_device<T>(side, stored_lower, trans, unit, m, h, A11, lda, B1, ldb, s);
+}
+
+#define INST(T) template int trsm_inv_device<T>(int, int, int, int, int, int, const T *, int, T *, int, cudaStream_t);
+INST(float)
+INST(double)
+INST(cfloat)
+INST(cdouble)
+
+}  // namespace jb

@@ -47,6 +47,39 @@ def test_trsm_row_major_and_large(gpu, blas, rng, t):
 
 
 @pytest.mark.parametrize("t", "sdcz")
+@pytest.mark.parametrize("side,uplo,trans,diag", list(itertools.product((141, 142), (121, 122), (111, 112, 113), (131, 132))))
+def test_trsm_gemm_form_all_variants(gpu, blas, rng, t, side, uplo, trans, diag):
+    """Wide solves take the GEMM form (inverted 64 x 64 diagonal blocks, csrc/trsm_inv.cu): triangle of order >= 128 against
+    >= 256 right-hand sides / rows, ragged last block, padded leading dimensions (NaN padding must stay NaN)."""
+    m, n = (200, 300) if side == 141 else (300, 200)
+    ka = m if side == 141 else n
+    A = tri_matrix(rng, t, ka, ka + 2)
+    B = rand(rng, t, m, n, m + 2)
+    alpha = 0.5 if t in "sd" else 0.5 - 0.25j
+    Bg, Bb = B.copy(order="F"), B.copy(order="F")
+    gpu.trsm(t, 102, side, uplo, trans, diag, m, n, alpha, A, ka + 2, Bg, m + 2)
+    blas.trsm(t, 102, side, uplo, trans, diag, m, n, alpha, A, ka + 2, Bb, m + 2)
+    assert fro(Bg[:m] - Bb[:m]) / fro(Bb[:m]) <= 200 * max(m, n) * EPS[t]
+    assert np.isnan(Bg[m:]).all()
+
+
+@pytest.mark.parametrize("t", "dc")
+@pytest.mark.parametrize("side,uplo,trans", list(itertools.product((141, 142), (121, 122), (111, 113))))
+def test_trsm_recursive_halving(gpu, blas, rng, t, side, uplo, trans):
+    """Triangles above 512 are halved recursively (one GEMM couples the halves) before the 64-row sweep runs: order 1100
+    (halves 576 + 524, the second halved again), ragged, every direction of the sweep."""
+    m, n = (1100, 260) if side == 141 else (260, 1100)
+    ka = m if side == 141 else n
+    A = tri_matrix(rng, t, ka, ka)
+    B = rand(rng, t, m, n, m + 2)
+    Bg, Bb = B.copy(order="F"), B.copy(order="F")
+    gpu.trsm(t, 102, side, uplo, trans, 131, m, n, 1.0, A, ka, Bg, m + 2)
+    blas.trsm(t, 102, side, uplo, trans, 131, m, n, 1.0, A, ka, Bb, m + 2)
+    assert fro(Bg[:m] - Bb[:m]) / fro(Bb[:m]) <= 200 * max(m, n) * EPS[t]
+    assert np.isnan(Bg[m:]).all()
+
+
+@pytest.mark.parametrize("t", "sdcz")
 @pytest.mark.parametrize("uplo", [121, 122])
 @pytest.mark.parametrize("trans", [111, 112])
 def test_syrk_herk(gpu, blas, rng, t, uplo, trans):

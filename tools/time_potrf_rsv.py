@@ -1,0 +1,27 @@
+"""dpotrf with different numbers of SMs kept free of the persistent GEMM during the look-ahead (potrf.reserve_sms)."""
+import ctypes as C, sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from jalla_b200._lib import lib, check
+check(lib.jb_init(0), "init")
+lib.jb_set_stream(C.c_void_p(torch.cuda.current_stream().cuda_stream))
+def ev(fn, reps):
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+for n in (8192, 16384):
+    A0 = torch.empty(n * n, dtype=torch.float64, device="cuda"); A = torch.empty_like(A0)
+    tc = ev(lambda: A.copy_(A0), 3)
+    check(lib.jb_dfill_uniform(A0.data_ptr(), n, n, n, 0, 0, 2, 1, float(n)), "fill")
+    def potrf(): A.copy_(A0); assert lib.LAPACKE_dpotrf(102, b"L", n, A.data_ptr(), n) == 0
+    for nb2, split in ((256, 0), (512, 0), (256, 1), (512, 1), (1024, 1)):
+        lib.jb_set_option(b"potrf.nb2", nb2); lib.jb_set_option(b"potrf.split", split)
+        out = []
+        for rsv in [int(x) for x in sys.argv[1:]] or [0, 4, 8, 12, 16, 24, 32]:
+            lib.jb_set_option(b"potrf.reserve_sms", rsv)
+            t = ev(potrf, 3) - tc
+            out.append("%d: %.2f" % (rsv, t))
+        print("n=%d nb2=%d split=%d  reserve_sms: ms  " % (n, nb2, split) + " | ".join(out), flush=True)
