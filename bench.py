@@ -277,9 +277,60 @@ def factorisations(torch, lib, check, stream):
         out[f"n{n}"] = {"dgetrf_ms": t_getrf, "dgetrf_tflops": f_lu / t_getrf / 1e9, "dgetrf_frac_of_dmma_peak": f_lu / t_getrf / 1e9 / DMMA_PEAK_TFLOPS,
                         "dgesv_nrhs1_ms": t_gesv, "dpotrf_ms": t_potrf, "dpotrf_tflops": f_ch / t_potrf / 1e9,
                         "dpotrf_frac_of_dmma_peak": f_ch / t_potrf / 1e9 / DMMA_PEAK_TFLOPS}
+        if n == 8192:
+            # invert (Matrix.hs:537-540: getrf + getri) and the level-3 triangular solve both run on the GEMM-form trsm
+            check(lib.jb_dfill_uniform(A0.data_ptr(), n, n, n, 0, 0, SEED, 0, 0.0), "fill")
+
+            def invert():
+                A.copy_(A0)
+                assert lib.LAPACKE_dgetrf(102, n, n, A.data_ptr(), n, piv.data_ptr()) == 0
+                assert lib.LAPACKE_dgetri(102, n, A.data_ptr(), n, piv.data_ptr()) == 0
+            t_inv = ev(invert, reps=1) - t_copy
+            B = torch.empty(n * n, dtype=torch.float64, device="cuda")
+            check(lib.jb_dfill_uniform(A0.data_ptr(), n, n, n, 0, 0, SEED + 3, 1, float(n)), "fill")
+
+            def trsm():
+                B.copy_(A0); lib.cblas_dtrsm(102, 141, 122, 111, 131, n, n, 1.0, A0.data_ptr(), n, B.data_ptr(), n)
+            t_trsm = ev(trsm) - t_copy
+            out[f"n{n}"].update({"dgetrf_dgetri_ms": t_inv, "dgetrf_dgetri_tflops": 2.0 * n ** 3 / t_inv / 1e9,
+                                 "dtrsm_LLNN_nrhs8192_ms": t_trsm, "dtrsm_tflops": float(n) ** 3 / t_trsm / 1e9})
+            del B
         del A0, A, b0, b, piv
         torch.cuda.empty_cache()
     return out
+
+
+def batched_cholesky(torch, lib, check, stream, hbm_gbs, batch=LU_BATCH, n=LU_N):
+    """The SPD sibling of configs[2]: jb_dpotrf_batched + jb_dpotrs_batched (nrhs = 1) on `batch` 32 x 32 Double systems, lower
+    storage; algorithmic bytes = the stored triangle in and out (potrf), the triangle in and b in / x out (potrs)."""
+    G = torch.empty(batch * n * n, dtype=torch.float64, device="cuda")
+    check(lib.jb_dfill_uniform(G.data_ptr(), n, n, batch * n, 0, 0, SEED + 5, 0, 0.0), "fill")
+    Gv = G.view(batch, n, n)
+    S0 = (torch.bmm(Gv, Gv.transpose(1, 2)) / n + torch.eye(n, dtype=torch.float64, device="cuda")).contiguous().view(-1)
+    del G, Gv
+    A = torch.empty_like(S0)
+    b0 = torch.empty(batch * n, dtype=torch.float64, device="cuda"); b = torch.empty_like(b0)
+    check(lib.jb_dfill_uniform(b0.data_ptr(), n, n, batch, 0, 0, SEED + 6, 0, 0.0), "fill")
+    info = torch.empty(batch, dtype=torch.int32, device="cuda")
+    t_f = t_s = 0.0
+    reps = 3
+    for r in range(reps + 1):
+        A.copy_(S0); b.copy_(b0)
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record(stream)
+        check(lib.jb_dpotrf_batched(b"L", n, A.data_ptr(), n, n * n, info.data_ptr(), batch), "potrf_batched")
+        e1.record(stream)
+        check(lib.jb_dpotrs_batched(b"L", n, 1, A.data_ptr(), n, n * n, b.data_ptr(), n, n, batch), "potrs_batched")
+        e2.record(stream); torch.cuda.synchronize()
+        if r:
+            t_f += e0.elapsed_time(e1) / reps; t_s += e1.elapsed_time(e2) / reps
+    assert int(info.abs().max().item()) == 0
+    tri = n * (n + 1) // 2 * 8
+    by_f, by_s = 2 * tri, tri + 2 * n * 8
+    return {"workload": f"{batch} SPD 32x32 Double systems, jb_dpotrf_batched + jb_dpotrs_batched (nrhs = 1), lower storage",
+            "potrf_ms": t_f, "potrs_ms": t_s, "solves_per_s": batch / ((t_f + t_s) * 1e-3),
+            "potrf_frac_of_hbm": batch * by_f / t_f / 1e6 / hbm_gbs, "potrs_frac_of_hbm": batch * by_s / t_s / 1e6 / hbm_gbs,
+            "algorithmic_bytes_per_system": {"potrf": by_f, "potrs": by_s}}
 
 
 def cholesky_config3(torch, lib, grid, dist, n=65536, nb=1024):
@@ -536,6 +587,7 @@ def main():
         torch.cuda.empty_cache()
     if world == 1 and args.only == "" and not args.no_other:
         out["factorisations"] = factorisations(torch, lib, check, stream)
+        out["batched_cholesky"] = batched_cholesky(torch, lib, check, stream, measured_peaks()[0])
     if world == 8 and args.only == "" and not args.no_other:
         gemm.close()
         del gemm

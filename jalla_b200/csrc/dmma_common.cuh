@@ -83,17 +83,20 @@ inline int make_map_f64(CUtensorMap *map, const void *ptr, long rows, long cols,
 // CTA and launch in total.  Square tiles (BM == BN) assumed for the triangle test.
 template <int GROUP_M>
 struct TileWalker {
-  int tiles_m, tiles_n, tri;
+  int tiles_m, tiles_n, tri, balanced;
   int band = 0, tn = 0, base = 0;       // cursor: kept tiles before column tn of this band
-  __device__ TileWalker(int tm_, int tn_, int tri_) : tiles_m(tm_), tiles_n(tn_), tri(tri_) {}
-  // coordinates of the idx-th tile of the sequence (idx must not decrease between calls); false when past the end
-  __device__ __forceinline__ bool at(int idx, int &tm_out, int &tn_out) {
-    if (tri == 0) {
-      if (idx >= tiles_m * tiles_n) return false;
+  __device__ TileWalker(int tm_, int tn_, int tri_, int balanced_ = 1) : tiles_m(tm_), tiles_n(tn_), tri(tri_), balanced(balanced_) {}
+  // coordinates of the idx-th tile of the sequence (idx must not decrease between calls); 0 when past the end, 1 = compute,
+  // 2 = skip (only with balanced == 0: the round-1 order, every tile in the sequence and the unwanted ones skipped)
+  __device__ __forceinline__ int at(int idx, int &tm_out, int &tn_out) {
+    if (tri == 0 || !balanced) {
+      if (idx >= tiles_m * tiles_n) return 0;
       const int per_band = GROUP_M * tiles_n, b = idx / per_band, in_band = idx % per_band;
       const int first_m = b * GROUP_M, gsz = min(tiles_m - first_m, GROUP_M);
       tm_out = first_m + in_band % gsz; tn_out = in_band / gsz;
-      return true;
+      if (tri == 'L' && tm_out < tn_out) return 2;
+      if (tri == 'U' && tn_out < tm_out) return 2;
+      return 1;
     }
     while (band * GROUP_M < tiles_m) {
       const int first_m = band * GROUP_M, end_m = min(tiles_m, first_m + GROUP_M);
@@ -101,11 +104,11 @@ struct TileWalker {
       const int lo = tri == 'L' ? max(first_m, tn) : first_m;
       const int hi = tri == 'L' ? end_m : min(end_m, tn + 1);
       const int cnt = max(hi - lo, 0);
-      if (idx < base + cnt) { tm_out = lo + (idx - base); tn_out = tn; return true; }
+      if (idx < base + cnt) { tm_out = lo + (idx - base); tn_out = tn; return 1; }
       base += cnt;
       if (++tn == tiles_n) { tn = 0; ++band; }
     }
-    return false;
+    return 0;
   }
 };
 

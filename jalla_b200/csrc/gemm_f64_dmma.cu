@@ -52,7 +52,7 @@ static_assert(BM == BN, "TileWalker's triangle test assumes square tiles");
 template <bool A_KM, bool B_KM>
 __global__ void __launch_bounds__(THREADS, 1)
 dgemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int m, int n, int k,
-                  double alpha, double beta, double *__restrict__ C, int ldc, int tri) {
+                  double alpha, double beta, double *__restrict__ C, int ldc, int tri, int balanced) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // 128B swizzle atoms need 1024B alignment
   const uint32_t bar_full = base + STAGES * STAGE_BYTES;            // STAGES x 8 bytes
@@ -81,9 +81,10 @@ dgemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       // tile's C columns over the main loop instead, so the epilogue reads hit L2.
       const bool pf = beta != 0.0 && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && ((ldc & 1) == 0);
       const int pf_step = (BN + KT - 1) / KT;
-      TileWalker<GROUP_M> walk(tiles_m, tiles_n, tri);
+      TileWalker<GROUP_M> walk(tiles_m, tiles_n, tri, balanced);
       int tm, tn;
-      for (int tile = blockIdx.x; walk.at(tile, tm, tn); tile += gridDim.x) {
+      for (int tile = blockIdx.x, st; (st = walk.at(tile, tm, tn)) != 0; tile += gridDim.x) {
+        if (st == 2) continue;
         int pf_col = 0;
         const int pf_cols = min(BN, n - tn * BN);
         const uint32_t pf_bytes = (uint32_t)(min(BM, m - tm * BM) * 8) & ~15u;
@@ -129,9 +130,10 @@ dgemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   int stage = 0; uint32_t phase = 0;
   const bool beta0 = (beta == 0.0);
 
-  TileWalker<GROUP_M> walk(tiles_m, tiles_n, tri);
+  TileWalker<GROUP_M> walk(tiles_m, tiles_n, tri, balanced);
   int tm, tn;
-  for (int tile = blockIdx.x; walk.at(tile, tm, tn); tile += gridDim.x) {
+  for (int tile = blockIdx.x, st; (st = walk.at(tile, tm, tn)) != 0; tile += gridDim.x) {
+    if (st == 2) continue;
     double acc[8][4][2];
 #pragma unroll
     for (int i = 0; i < 8; i++)
@@ -222,7 +224,7 @@ static int launch(const CUtensorMap &ma, const CUtensorMap &mb, int m, int n, in
   if (cap > 0 && cap < grid) grid = cap;
   const int tcap = tls().gemm_cta_cap;          // set by the look-ahead factorisations around their trailing update
   if (tcap > 0 && tcap < grid) grid = tcap;
-  dgemm_dmma_kernel<A_KM, B_KM><<<grid, THREADS, SMEM_BYTES, s>>>(ma, mb, m, n, k, alpha, beta, C, ldc, tri);
+  dgemm_dmma_kernel<A_KM, B_KM><<<grid, THREADS, SMEM_BYTES, s>>>(ma, mb, m, n, k, alpha, beta, C, ldc, tri, option("gemm.tri_balance") != 0);
   count_launch();
   JB_CUDA(cudaGetLastError());
   return 1;

@@ -1501,7 +1501,7 @@ static int potrf_panels(char uplo, int n, T *A, int lda, int *d_info, int NB2, c
           const double mt = (double)(n - c0 - jn), up_flop = mt * mt * jb2 * (Num<T>::cplx ? 4.0 : 1.0);
           const int G = (n - c0 - NB + (CHOL_PANEL_THREADS - NB) - 1) / (CHOL_PANEL_THREADS - NB);
           double best = 1e30;
-          for (int r : {8, 16, 24, 32, 48, 64}) {
+          for (int r : {24, 32, 48, 64}) {      // below 24 the chain's skinny updates starve (16384: 65.6 ms at 16, 64.6 at 24)
             const double t_up = up_flop / (0.182e6 * (num_sms() - r));
             const double t_chain = (jn / (double)NB) * (((G + r - 1) / r) * 21.0 + 35.0);
             const double t = t_up > t_chain ? t_up : t_chain;
