@@ -7,6 +7,7 @@
 // kernel, the block row is solved against the unit-lower diagonal block, and the trailing
 // matrix is updated by this library's own GEMM (gemm_device: DMMA for double).
 #include "jb_common.cuh"
+#include <vector>
 #include <atomic>
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
@@ -266,13 +267,17 @@ __device__ __forceinline__ void warp_best(unsigned long long key, int row, bool 
 
 constexpr int PANEL_REC_PER_LANE = 5;     // the record poll covers G <= 160 CTAs
 constexpr int PANEL_MULTI_THREADS = 256;  // rows per CTA of the multi-CTA instantiation (registers to spare)
+// Second multi-CTA instantiation: 512 rows per CTA for at most 32 CTAs (one record per lane, 128 registers).  Half the
+// CTAs for the same panel: a panel of 8k-16k rows then needs <= 32 co-resident CTAs, few enough to run one block ahead
+// of the trailing update (getrf_device).  Not for complex double (the multipliers would need 256 KB of shared memory).
+constexpr int PANEL_WIDE_THREADS = 512, PANEL_WIDE_MAX_CTAS = 32;
 
 // A panel row as it is passed around: `rot` is the owner's register image (rot[j] = panel column c+j at step c, so
 // every access is a static, 16-byte aligned pair), `lpart` its multipliers in absolute columns 0..c-1.
 template <typename T> struct alignas(16) PanelRow { T rot[NB]; T lpart[NB]; };
 template <typename T> struct alignas(2 * sizeof(T)) PanelPair { T x, y; };
 
-template <typename T, int MAXT, bool MULTI>
+template <typename T, int MAXT, bool MULTI, int RPL = PANEL_REC_PER_LANE>
 __global__ void __launch_bounds__(MAXT, 1)
 lu_panel_reg_kernel(int pm, int jb, T *__restrict__ Pg, int ldg, int *__restrict__ ipiv, int *info, int row_off,
                     PanelLLScratch sc, unsigned tag0) {
@@ -357,10 +362,10 @@ lu_panel_reg_kernel(int pm, int jb, T *__restrict__ Pg, int ldg, int *__restrict
         int gr = NONE;
         {
           bool ok;
-          unsigned long long w0[PANEL_REC_PER_LANE], w1[PANEL_REC_PER_LANE], w2[PANEL_REC_PER_LANE];
+          unsigned long long w0[RPL], w1[RPL], w2[RPL];
           do {
 #pragma unroll
-            for (int i = 0; i < PANEL_REC_PER_LANE; i++) {
+            for (int i = 0; i < RPL; i++) {
               const int g = lane + 32 * i;
               if (g < G) {
                 const unsigned long long *rg = sc.rec + ((size_t)par * G + g) * 4;
@@ -371,12 +376,12 @@ lu_panel_reg_kernel(int pm, int jb, T *__restrict__ Pg, int ldg, int *__restrict
             }
             ok = true;
 #pragma unroll
-            for (int i = 0; i < PANEL_REC_PER_LANE; i++)
+            for (int i = 0; i < RPL; i++)
               if (lane + 32 * i < G)
                 ok = ok && (unsigned)(w0[i] >> 32) == tag && (unsigned)(w1[i] >> 32) == tag && (unsigned)(w2[i] >> 32) == tag;
           } while (!ok);
 #pragma unroll
-          for (int i = 0; i < PANEL_REC_PER_LANE; i++)
+          for (int i = 0; i < RPL; i++)
             if (lane + 32 * i < G) {
               const unsigned long long k = ((unsigned long long)(unsigned)w0[i] << 32) | (unsigned)w1[i];
               const int r = (int)(unsigned)w2[i];
@@ -918,7 +923,7 @@ __global__ void permute_rows_kernel(int inverse, int n, int nrhs, const int *__r
 template <typename T> struct PanelMaxThreads { static constexpr int value = sizeof(T) == 16 ? 256 : 512; };
 struct PanelCtx {
   int variant = 0;            // 0: rows-in-registers panel kernel, 1: the shared-memory panel kernels
-  int panel_rows = 256;       // rows (= threads) per CTA of the cooperative register panel
+  int panel_rows = 0;         // rows (= threads) per CTA of the cooperative register panel; 0 = 256, or 512 where that makes <= 32 CTAs of > 32
   int coop_min_rows = 1024;   // shared-memory kernels: from this many rows on, the multi-CTA one
   PanelScratch sc{};
   bool have_sc = false;
@@ -956,6 +961,17 @@ static unsigned next_panel_tag() {
   return seq.fetch_add(1) * 64u + 1u;
 }
 
+// Rows per CTA of the cooperative register panel for a panel of pm rows (0: not the cooperative register panel).
+template <typename T>
+static int panel_rows_for(int pm, const PanelCtx &ctx, int nsm) {
+  const bool wide_ok = sizeof(T) < 16 && (pm + PANEL_WIDE_THREADS - 1) / PANEL_WIDE_THREADS <= PANEL_WIDE_MAX_CTAS;
+  if (wide_ok && (ctx.panel_rows == PANEL_WIDE_THREADS || (ctx.panel_rows == 0 && pm > PANEL_WIDE_MAX_CTAS * PANEL_MULTI_THREADS)))
+    return PANEL_WIDE_THREADS;
+  int nt = ctx.panel_rows <= 0 || ctx.panel_rows > PANEL_MULTI_THREADS ? PANEL_MULTI_THREADS : ctx.panel_rows;
+  while ((pm + nt - 1) / nt > nsm && nt < PANEL_MULTI_THREADS) nt *= 2;
+  return nt;
+}
+
 // One level of the right-looking LU with NB = 32 panels on the m x n block at A, whose first row is row
 // `row_base` of the caller's matrix (ipiv / info are written in the caller's numbering; d_ipiv is indexed locally).
 template <typename T>
@@ -975,8 +991,7 @@ static int getrf_nb32(int m, int n, T *A, int lda, int *d_ipiv, int *d_info, int
     if (ctx.variant == 0) {
       if (pm <= MAXT) { reg_nt = ((pm + 31) / 32) * 32; reg_G = 1; }
       else if (ctx.have_ll) {
-        reg_nt = ctx.panel_rows > PANEL_MULTI_THREADS ? PANEL_MULTI_THREADS : ctx.panel_rows;
-        while ((pm + reg_nt - 1) / reg_nt > nsm && reg_nt < PANEL_MULTI_THREADS) reg_nt *= 2;
+        reg_nt = panel_rows_for<T>(pm, ctx, nsm);
         reg_G = (pm + reg_nt - 1) / reg_nt;
         if (reg_G > nsm || reg_G < 2) reg_G = 0;      // taller than 148 x 256 rows: the shared-memory kernels
       }
@@ -992,8 +1007,10 @@ static int getrf_nb32(int m, int n, T *A, int lda, int *d_ipiv, int *d_info, int
         lu_panel_reg_kernel<T, MAXT, false><<<1, reg_nt, shm, s>>>(pmm, jbb, Pp, ldp, pv, d_info, roff, ll, tag0);
       } else {
         void *args[] = {&pmm, &jbb, &Pp, &ldp, &pv, &d_info, &roff, &ll, &tag0};
-        JB_CUDA(cudaLaunchCooperativeKernel((void *)lu_panel_reg_kernel<T, PANEL_MULTI_THREADS, true>, dim3(reg_G),
-                                            dim3(reg_nt), args, shm, s));
+        void *fn = (void *)lu_panel_reg_kernel<T, PANEL_MULTI_THREADS, true>;
+        if constexpr (sizeof(T) < 16)
+          if (reg_nt == PANEL_WIDE_THREADS) fn = (void *)lu_panel_reg_kernel<T, PANEL_WIDE_THREADS, true, 1>;
+        JB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(reg_G), dim3(reg_nt), args, shm, s));
       }
       count_launch();
     } else if (have_scratch && pm >= coop_min_rows) {
@@ -1042,6 +1059,69 @@ template <typename T>
 static int trsm_left_blocked(int stored_lower, int trans, int unit, int n, int nrhs, const T *A, int lda, T *B, int ldb,
                              cudaStream_t s);
 
+// Middle level of the blocked LU: an outer block of n (<= NB2) columns is factorised in sub-blocks of `nbm` columns.  The
+// rank-32 updates of getrf_nb32 then stay inside a sub-block, and the rest of the outer block takes ONE rank-nbm update
+// per sub-block: the skinny updates, which only stream C (rows x remaining columns, read and written per 32 columns),
+// move 2.5x fewer bytes at nbm = 128, NB2 = 512 — they were half of the look-ahead chain's duration
+// (profiles/trace_getrf16384_r2c.txt).  An entry's update is now accumulated nbm products at a time instead of 32 (same k
+// order, different rounding points), like any change of block size.  Numbering as getrf_nb32: A points at the block, `row_base` is its first row
+// in the caller's matrix, d_ipiv is indexed locally and holds caller-numbered rows.
+template <typename T>
+static int getrf_mid(int m, int n, T *A, int lda, int *d_ipiv, int *d_info, int row_base, const PanelCtx &ctx, int nbm, cudaStream_t s) {
+  const int mn = m < n ? m : n;
+  if (nbm < 2 * NB || mn <= nbm + NB) return getrf_nb32<T>(m, n, A, lda, d_ipiv, d_info, row_base, ctx, s);
+  const T minus1 = Num<T>::neg(Num<T>::one()), one = Num<T>::one();
+  for (int j0 = 0; j0 < mn; j0 += nbm) {
+    const int jb = (mn - j0 < nbm) ? (mn - j0) : nbm;
+    if (int rc = getrf_nb32<T>(m - j0, jb, A + j0 + (size_t)j0 * lda, lda, d_ipiv + j0, d_info, row_base + j0, ctx, s)) return rc;
+    const int c0 = j0 + jb;
+    if (c0 < n) {                // columns of the block right of the sub-block: interchanges, block-row solve, rank-jb update
+      if (int rc = laswp_launch<T>(A, lda, c0, n, d_ipiv, j0, c0, row_base, s)) return rc;
+      if (int rc = trsm_left_blocked<T>(1, 111, 1, jb, n - c0, A + j0 + (size_t)j0 * lda, lda, A + j0 + (size_t)c0 * lda, lda, s)) return rc;
+      if (m - c0 > 0)
+        if (int rc = gemm_device<T>(111, 111, m - c0, n - c0, jb, minus1, A + c0 + (size_t)j0 * lda, lda, A + j0 + (size_t)c0 * lda, lda, one,
+                                    A + c0 + (size_t)c0 * lda, lda, s, 0)) return rc;
+    }
+  }
+  // the finished sub-blocks on the left take the later sub-blocks' interchanges in one pass per sub-block boundary
+  for (int j0 = nbm; j0 < mn; j0 += nbm) {
+    const int jb = (mn - j0 < nbm) ? (mn - j0) : nbm;
+    if (int rc = laswp_launch<T>(A, lda, 0, j0, d_ipiv, j0, j0 + jb, row_base, s)) return rc;
+  }
+  return 0;
+}
+
+// Debug timeline of a look-ahead factorisation (options getrf.trace / potrf.trace): timing events at the four points of
+// every outer step, printed to stderr after a final synchronisation.  Off: no events are created.
+struct StepTrace {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;      // per step: start (s), first block updated (s), chain end (s2), update end (s)
+  std::vector<int> tag;
+  void mark(cudaStream_t st, int t) {
+    if (!on) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, st);
+    ev.push_back(e); tag.push_back(t);
+  }
+  void print(const char *what, cudaStream_t s) {
+    if (!on || ev.empty()) return;
+    cudaStreamSynchronize(s);
+    double sum[3] = {0, 0, 0}, crit = 0;
+    for (size_t i = 0; i + 3 < ev.size(); i += 4) {
+      float a = 0, b = 0, c = 0;
+      cudaEventElapsedTime(&a, ev[i], ev[i + 1]);
+      cudaEventElapsedTime(&b, ev[i + 1], ev[i + 2]);
+      cudaEventElapsedTime(&c, ev[i + 1], ev[i + 3]);
+      fprintf(stderr, "[%s.trace] J0=%5d first %.3f ms | chain %.3f | rest update %.3f\n", what, tag[i], a, b, c);
+      sum[0] += a; sum[1] += b; sum[2] += c; crit += a + (b > c ? b : c);
+    }
+    fprintf(stderr, "[%s.trace] sums: first %.2f ms, chain %.2f, rest update %.2f, critical path %.2f\n", what, sum[0], sum[1], sum[2], crit);
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    ev.clear(); tag.clear();
+  }
+};
+
 // Two-level right-looking LU: outer panels of NB2 columns are factorised by the NB=32 routine (tall panels on the
 // cooperative multi-CTA kernel); the interchanges, the unit-lower block-row solve and ONE rank-NB2 GEMM update per
 // outer step then touch the rest of the matrix — NB2/32 times fewer sweeps over the trailing matrix.
@@ -1057,10 +1137,13 @@ int getrf_device(int m, int n, T *A, int lda, int *d_ipiv, int *d_info, cudaStre
                                (int)((size_t)NB * MAXT * sizeof(T))));
   JB_CUDA(cudaFuncSetAttribute(lu_panel_reg_kernel<T, PANEL_MULTI_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)((size_t)NB * PANEL_MULTI_THREADS * sizeof(T))));
+  if constexpr (sizeof(T) < 16)
+    JB_CUDA(cudaFuncSetAttribute(lu_panel_reg_kernel<T, PANEL_WIDE_THREADS, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)((size_t)NB * PANEL_WIDE_THREADS * sizeof(T))));
   constexpr int W = sizeof(T) / 4;
   PanelCtx ctx;
   ctx.variant = option("getrf.panel_variant") > 0 ? 1 : 0;
-  if (option("getrf.panel_rows") > 0) ctx.panel_rows = (option("getrf.panel_rows") + 31) / 32 * 32;
+  if (option("getrf.panel_rows") > 0) ctx.panel_rows = (option("getrf.panel_rows") + 31) / 32 * 32;      // 512: the wide instantiation wherever it fits
   if (option("getrf.coop_min_rows") > 0) ctx.coop_min_rows = option("getrf.coop_min_rows");
   unsigned char *scratch = nullptr, *scratch_ll = nullptr;
   if (ctx.variant == 0 && m > MAXT) {
@@ -1096,6 +1179,11 @@ int getrf_device(int m, int n, T *A, int lda, int *d_ipiv, int *d_info, cudaStre
   // with look-ahead (tools/time_nb2_potrf.py): 4096: 13.8 / 14.5 / 14.6 ms for 128 / 256 / 512; 8192: 39.7 / 37.3 / 36.9;
   // 16384: 181.7 / 165.2 / 158.5; 2048 stays single level (5.6 ms against 6.5)
   if (NB2 <= 0) NB2 = (mn >= 8192) ? 512 : (mn >= 4096 ? 128 : mn);
+  // sub-block width inside an outer block (getrf_mid); 0 = none.  Measured (profiles/lookahead_r2c.jsonl): no gain for LU —
+  // 16384: 145.1 / 143.4 ms at 128 / 256 against 144.4 without, 8192: 36.0 / 34.7 against 33.9 (the chain is the
+  // cooperative panel kernel itself, and every sub-block adds an interchange and a solve launch) — off by default.
+  int nbm = option("getrf.nbm");
+  if (nbm < 0) nbm = 0;
   int rc = 0;
   if (mn <= NB2 + NB) {
     rc = getrf_nb32<T>(m, n, A, lda, d_ipiv, d_info, 0, ctx, s);
@@ -1110,58 +1198,101 @@ int getrf_device(int m, int n, T *A, int lda, int *d_ipiv, int *d_info, cudaStre
     if (lookahead) if (int r = la.open()) { ws_free(scratch, s); ws_free(scratch_ll, s); return r; }
     cudaStream_t s2 = la.s2;
     cudaEvent_t ev_first = la.ev_first, ev_panel = la.ev_panel;
-    // right-of-block work of outer step (J0, jb2) on columns [c0, c1): interchanges, U12 solve, rank-jb2 update
-    auto right_update = [&](int J0, int jb2, int c0, int c1, cudaStream_t st) -> int {
+    // right-of-block work of outer step (J0, jb2) on columns [c0, c1): interchanges + U12 solve, then the rank-jb2 update
+    auto right_solve = [&](int J0, int jb2, int c0, int c1, cudaStream_t st) -> int {
       if (c1 <= c0) return 0;
       int r = laswp_launch<T>(A, lda, c0, c1, d_ipiv, J0, J0 + jb2, 0, st);
       if (!r) r = trsm_left_blocked<T>(1, 111, 1, jb2, c1 - c0, A + J0 + (size_t)J0 * lda, lda, A + J0 + (size_t)c0 * lda, lda, st);
-      const int mr = m - J0 - jb2;
-      if (!r && mr > 0)
-        r = gemm_device<T>(111, 111, mr, c1 - c0, jb2, minus1, A + (J0 + jb2) + (size_t)J0 * lda, lda,
-                           A + J0 + (size_t)c0 * lda, lda, one, A + (J0 + jb2) + (size_t)c0 * lda, lda, st, 0);
       return r;
     };
+    auto right_gemm = [&](int J0, int jb2, int c0, int c1, cudaStream_t st) -> int {
+      const int mr = m - J0 - jb2;
+      if (c1 <= c0 || mr <= 0) return 0;
+      return gemm_device<T>(111, 111, mr, c1 - c0, jb2, minus1, A + (J0 + jb2) + (size_t)J0 * lda, lda,
+                            A + J0 + (size_t)c0 * lda, lda, one, A + (J0 + jb2) + (size_t)c0 * lda, lda, st, 0);
+    };
+    auto right_update = [&](int J0, int jb2, int c0, int c1, cudaStream_t st) -> int {
+      int r = right_solve(J0, jb2, c0, c1, st);
+      return r ? r : right_gemm(J0, jb2, c0, c1, st);
+    };
     bool factored = false;                      // block at J0 already factorised by the previous step's look-ahead
+    StepTrace tr;
+    tr.on = lookahead && option("getrf.trace") > 0;
     for (int J0 = 0; J0 < mn && !rc; J0 += NB2) {
       const int jb2 = (mn - J0 < NB2) ? (mn - J0) : NB2;
+      tr.mark(s, J0);
       if (!factored)
-        rc = getrf_nb32<T>(m - J0, jb2, A + J0 + (size_t)J0 * lda, lda, d_ipiv + J0, d_info, J0, ctx, s);
+        rc = getrf_mid<T>(m - J0, jb2, A + J0 + (size_t)J0 * lda, lda, d_ipiv + J0, d_info, J0, ctx, nbm, s);
       factored = false;
       if (rc) break;
-      if (J0 > 0) rc = laswp_launch<T>(A, lda, 0, J0, d_ipiv, J0, J0 + jb2, 0, s);
-      if (rc) break;
       const int c0 = J0 + jb2;
-      if (n - c0 <= 0) break;
       const int jn = (c0 < mn) ? ((mn - c0 < NB2) ? (mn - c0) : NB2) : 0;      // width of the next block
       const int mr = m - c0;
-      if (lookahead && jn > 0 && mr > 0) {
+      const bool ahead = lookahead && jn > 0 && mr > 0 && n - c0 > 0;
+      // the interchanges of the finished columns on the left are read by nobody in this sweep: behind the chain's start
+      if (J0 > 0 && !ahead) rc = laswp_launch<T>(A, lda, 0, J0, d_ipiv, J0, J0 + jb2, 0, s);
+      if (rc) break;
+      if (n - c0 <= 0) break;
+      if (ahead) {
         rc = right_update(J0, jb2, c0, c0 + jn, s);
         if (rc) break;
         JB_CUDA(cudaEventRecord(ev_first, s));
         JB_CUDA(cudaStreamWaitEvent(s2, ev_first, 0));
-        rc = getrf_nb32<T>(m - c0, jn, A + c0 + (size_t)c0 * lda, lda, d_ipiv + c0, d_info, c0, ctx, s2);
+        tr.mark(s, J0);
+        if (J0 > 0) rc = laswp_launch<T>(A, lda, 0, J0, d_ipiv, J0, J0 + jb2, 0, s);
+        if (rc) break;
+        // CTAs the panel phase needs at once: the cooperative panel grid or one CTA, + room for its interchange /
+        // small-solve / small-GEMM launches.  The persistent GEMM of the trailing update is capped to leave them free —
+        // but only for as many columns as the panel chain is expected to last (model below); the remaining columns run
+        // as a second, uncapped launch.  (Capping the whole update costs need/148 of ALL of it: reserving 70 SMs at
+        // n = 16384 lost more GEMM time than the panels hid, 175 -> 201 ms.)
+        // (The chain's own rank-32 updates stay uncapped: their CTAs run in waves over whatever SMs are free and spread
+        // out as soon as the trailing update ends; capping them to the reserved SMs measured 0-1 ms slower.)
+        constexpr int MAXT = PanelMaxThreads<T>::value;
+        const int prow = panel_rows_for<T>(mr, ctx, nsm);
+        int need = (mr > MAXT ? (mr + prow - 1) / prow : 1) + 8;
+        int max_need = option("getrf.la_max_need");
+        if (max_need <= 0) max_need = 80;
+        const int cA = c0 + jn;
+        const bool overlap = need <= max_need && nsm - need >= 32;
+        int scale = option("getrf.la_chain_pct");
+        if (scale <= 0) scale = 115;
+        // chain of the next block: jn/32 steps of (32 columns at ~2 us (cooperative) or ~1 us (one CTA), the fused
+        // interchange/solve launch, a rank-32 update streaming mr x jn/2 entries)
+        const double t_chain = (jn / (double)NB) * (NB * (mr > MAXT ? 2.0 : 1.0) + 15.0 + 0.002 * mr) * scale * 0.01;
+        const double rate = (sizeof(T) == 4 || sizeof(T) == 8 && Num<T>::cplx ? 0.36e6 : 0.225e6);    // flop per us and SM on the update
+        const double flop_col = (Num<T>::cplx ? 8.0 : 2.0) * (double)(m - c0) * jb2;
+        const int chain_sms = need;
+        rc = getrf_mid<T>(m - c0, jn, A + c0 + (size_t)c0 * lda, lda, d_ipiv + c0, d_info, c0, ctx, nbm, s2);
         if (rc) break;
         JB_CUDA(cudaEventRecord(ev_panel, s2));
-        // CTAs the panel phase needs at once: the cooperative panel grid (256 rows each) or one CTA
-        constexpr int MAXT = PanelMaxThreads<T>::value;
-        int need = mr > MAXT ? (mr + PANEL_MULTI_THREADS - 1) / PANEL_MULTI_THREADS : 1;
-        need += 8;                              // + room for its interchange / small-solve / small-GEMM launches
-        // Measured: reserving 38 SMs pays at n = 8192 (43.0 -> 37.0 ms) but 70 SMs at n = 16384 cost more GEMM time
-        // than the panels hide (175 -> 201 ms).  Taller panels therefore run after the update, uncapped.
-        {
-          GemmCapScope cap(need <= 40 ? nsm - need : 0);
-          rc = right_update(J0, jb2, c0 + jn, n, s);
+        tr.mark(s2, J0);
+        if (overlap) {
+          long ncap = (long)(t_chain * rate * (nsm - chain_sms) / flop_col);
+          ncap = (ncap + 127) / 128 * 128;
+          if (ncap > n - cA - 256) ncap = n - cA;           // no sliver launches
+          {
+            GemmCapScope cap(nsm - chain_sms);
+            rc = right_solve(J0, jb2, cA, n, s);
+            if (!rc) rc = right_gemm(J0, jb2, cA, cA + (int)ncap, s);
+          }
+          if (!rc) rc = right_gemm(J0, jb2, cA + (int)ncap, n, s);
+        } else {
+          rc = right_update(J0, jb2, cA, n, s);
         }
+        tr.mark(s, J0);
         JB_CUDA(cudaStreamWaitEvent(s, ev_panel, 0));
         factored = true;
       } else {
         rc = right_update(J0, jb2, c0, n, s);
+        if (tr.on) { tr.mark(s, J0); tr.mark(s, J0); tr.mark(s, J0); }
       }
     }
     if (lookahead) {              // whatever path left the loop: nothing of the second stream outlives the call's stream order
       cudaEventRecord(ev_panel, s2);
       cudaStreamWaitEvent(s, ev_panel, 0);
     }
+    tr.print("getrf", s);
   }
   if (prof) {
     long long h[8];
@@ -1443,15 +1574,26 @@ static int potrf_panels(char uplo, int n, T *A, int lda, int *d_info, int NB2, c
   // split = true: only the rows of the diagonal block (a few CTAs); the rows below follow as ONE triangular solve in
   // GEMM form (trsm_inv.cu) — the block column below a 512-wide outer block is then 17 launches on the tuned GEMM instead
   // of 16 x (panel over all rows + skinny rank-32 update), and the look-ahead chain needs 8 free SMs instead of 16-64.
+  // Middle level (potrf.nbm, default 128): the rank-32 updates stay inside sub-blocks of nbm columns, the rest of the outer
+  // block takes one rank-nbm update per sub-block — the skinny updates only stream C, and this moves 2.5x fewer bytes at
+  // nbm = 128, NB2 = 512 (they were most of the look-ahead chain: profiles/trace_potrf16384_r2c.txt).  As with any change
+  // of block size an entry's update is accumulated in different groups (same k order, different rounding points).
+  int nbm = option("potrf.nbm");
+  if (nbm < 0) nbm = 128;
   auto factor_block = [&](int J0, int jb2, cudaStream_t st, bool split) -> int {
     const int r_end = split ? J0 + jb2 : n;
-    for (int j0 = J0; j0 < J0 + jb2; j0 += NB) {
-      const int jb = (J0 + jb2 - j0 < NB) ? (J0 + jb2 - j0) : NB;
-      const int m = r_end - j0;
-      const int G = m > NB ? (m - NB + (CHOL_PANEL_THREADS - NB) - 1) / (CHOL_PANEL_THREADS - NB) : 1;
-      chol_panel_kernel<T><<<G, CHOL_PANEL_THREADS, shm, st>>>(lower, m, jb, A + j0 + (size_t)j0 * lda, lda, d_info, j0, d_count);
-      count_launch();
-      if (int rc = update(j0 + jb, j0 + jb, J0 + jb2, j0, j0 + jb, st, r_end)) return rc;
+    const int sub = (nbm >= 2 * NB && jb2 > nbm + NB) ? nbm : jb2;
+    for (int S0 = J0; S0 < J0 + jb2; S0 += sub) {
+      const int S1 = (S0 + sub < J0 + jb2) ? S0 + sub : J0 + jb2;
+      for (int j0 = S0; j0 < S1; j0 += NB) {
+        const int jb = (S1 - j0 < NB) ? (S1 - j0) : NB;
+        const int m = r_end - j0;
+        const int G = m > NB ? (m - NB + (CHOL_PANEL_THREADS - NB) - 1) / (CHOL_PANEL_THREADS - NB) : 1;
+        chol_panel_kernel<T><<<G, CHOL_PANEL_THREADS, shm, st>>>(lower, m, jb, A + j0 + (size_t)j0 * lda, lda, d_info, j0, d_count);
+        count_launch();
+        if (int rc = update(j0 + jb, j0 + jb, S1, j0, j0 + jb, st, r_end)) return rc;
+      }
+      if (int rc = update(S1, S1, J0 + jb2, S0, S1, st, r_end)) return rc;
     }
     return 0;
   };
@@ -1473,8 +1615,11 @@ static int potrf_panels(char uplo, int n, T *A, int lda, int *d_info, int NB2, c
   cudaEvent_t ev_first = la.ev_first, ev_panel = la.ev_panel;
   int rc = 0;
   bool factored = false;
+  StepTrace tr;
+  tr.on = lookahead && option("potrf.trace") > 0;
   for (int J0 = 0; J0 < n && !rc; J0 += NB2) {
     const int jb2 = (n - J0 < NB2) ? (n - J0) : NB2;
+    tr.mark(s, J0);
     if (!factored) rc = factor_block(J0, jb2, s, split);
     factored = false;
     if (!rc && split) rc = solve_below(J0, jb2, s);
@@ -1487,40 +1632,72 @@ static int potrf_panels(char uplo, int n, T *A, int lda, int *d_info, int NB2, c
       if (rc) break;
       JB_CUDA(cudaEventRecord(ev_first, s));
       JB_CUDA(cudaStreamWaitEvent(s2, ev_first, 0));
-      rc = factor_block(c0, jn, s2, split);
-      if (rc) break;
-      JB_CUDA(cudaEventRecord(ev_panel, s2));
+      tr.mark(s, J0);
+      int rsv = option("potrf.reserve_sms");
+      const bool timed = option("potrf.timed_cap") != 0;
+      const int a0 = c0 + jn;
+      const double mt = (double)(n - a0), up_flop = mt * mt * jb2 * (Num<T>::cplx ? 4.0 : 1.0);
+      const double per_sm = 0.182e6;                  // flop per us and SM on the triangle update
+      const int G = (n - c0 - NB + (CHOL_PANEL_THREADS - NB) - 1) / (CHOL_PANEL_THREADS - NB);
+      auto chain_us = [&](int r) { return (jn / (double)NB) * (((G + r - 1) / r) * 21.0 + 35.0); };
       {
         // SMs kept free of the persistent GEMM for the panel chain of the next block.  Unsplit, the chain runs its G
         // independent panel CTAs in waves over the free SMs, so it is as long as the update when few SMs face a tall panel,
         // and the update is longer than it has to be when many SMs wait for a short one: pick the split that balances the
         // two (model: update at ~0.18 TFLOP/s per SM, a panel wave 21 us, 35 us per 32-column step for the skinny update).
-        int rsv = option("potrf.reserve_sms");
         if (rsv < 0 && split) rsv = 8;
+        // timed: the cap holds only for the first columns of the update — as many as the chain is expected to last; the
+        // rest runs as a second, uncapped launch.  Measured (tools/time_lookahead.py, profiles/lookahead_r2c.jsonl): with
+        // the rank-32 chain of round 2b it lost (16384: 65.5 ms against 64.2 — the chain was as long as the update, and
+        // an uncapped launch that starts before the chain has ended takes its SMs); with the middle level the chain is
+        // shorter than the update and it wins a little (16384: 60.4 against 61.0, 8192: 12.97 / 12.92).
         if (rsv < 0) {
-          const double mt = (double)(n - c0 - jn), up_flop = mt * mt * jb2 * (Num<T>::cplx ? 4.0 : 1.0);
-          const int G = (n - c0 - NB + (CHOL_PANEL_THREADS - NB) - 1) / (CHOL_PANEL_THREADS - NB);
           double best = 1e30;
-          for (int r : {24, 32, 48, 64}) {      // below 24 the chain's skinny updates starve (16384: 65.6 ms at 16, 64.6 at 24)
-            const double t_up = up_flop / (0.182e6 * (num_sms() - r));
-            const double t_chain = (jn / (double)NB) * (((G + r - 1) / r) * 21.0 + 35.0);
-            const double t = t_up > t_chain ? t_up : t_chain;
+          for (int r : {24, 32, 48, 64, 96}) {      // below 24 the chain's skinny updates starve (16384: 65.6 ms at 16, 64.6 at 24)
+            if (!timed && r > 64) continue;
+            const double t_chain = chain_us(r), t_cap = up_flop / (per_sm * (num_sms() - r));
+            double t = t_cap > t_chain ? t_cap : t_chain;
+            if (timed && t_cap > t_chain) t = t_chain + (up_flop - t_chain * per_sm * (num_sms() - r)) / (per_sm * num_sms());
             if (t < best) { best = t; rsv = r; }
           }
         }
-        GemmCapScope cap(rsv > 0 ? num_sms() - rsv : 0);
-        rc = update(c0 + jn, c0 + jn, n, J0, c0, s);
       }
+      rc = factor_block(c0, jn, s2, split);      // its skinny updates stay uncapped (waves over the free SMs; capped: 66.3 against 64.2 ms at 16384)
+      if (rc) break;
+      JB_CUDA(cudaEventRecord(ev_panel, s2));
+      tr.mark(s2, J0);
+      {
+        int cs = n;                                      // columns [a0, cs) run capped
+        if (timed && rsv > 0) {
+          int pct = option("potrf.chain_pct");
+          if (pct <= 0) pct = 140;       // 16384: 61.2 / 60.2 / 59.5 ms at 80 / 110 / 140 %
+          const double f1 = chain_us(rsv) * pct * 0.01 * per_sm * (num_sms() - rsv) / (jb2 * (Num<T>::cplx ? 4.0 : 1.0));   // (n-a0)^2 - (n-cs)^2
+          const double left = mt * mt - f1;
+          if (left > 0) {
+            cs = n - (int)sqrt(left);
+            cs = a0 + (cs - a0 + 127) / 128 * 128;
+            if (cs > n - 512) cs = n;
+          }
+        }
+        {
+          GemmCapScope cap(rsv > 0 ? num_sms() - rsv : 0);
+          rc = update(a0, a0, cs, J0, c0, s);
+        }
+        if (!rc && cs < n) rc = update(cs, cs, n, J0, c0, s);
+      }
+      tr.mark(s, J0);
       JB_CUDA(cudaStreamWaitEvent(s, ev_panel, 0));
       factored = true;
     } else {
       rc = update(c0, c0, n, J0, c0, s);
+      if (tr.on) { tr.mark(s, J0); tr.mark(s, J0); tr.mark(s, J0); }
     }
   }
   if (lookahead) {
     cudaEventRecord(ev_panel, s2);
     cudaStreamWaitEvent(s, ev_panel, 0);
   }
+  tr.print("potrf", s);
   if (rc) return rc;
   JB_CUDA(cudaGetLastError());
   return 0;

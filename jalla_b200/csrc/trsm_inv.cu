@@ -122,7 +122,9 @@ int trsm_inv_device(int side, int stored_lower, int trans, int unit, int m, int 
   if (!Num<T>::cplx && trans == 113) trans = 112;
   const int nt = side == 141 ? m : n;
   // narrow right-hand sides leave the coupling GEMM too few tiles (n = 8192, nrhs = 512: 6.2 ms halved, 5.0 ms swept)
-  if (nt <= REC_BASE || (side == 141 ? n : m) < 1024) return trsm_inv_base<T>(side, stored_lower, trans, unit, m, n, A, lda, B, ldb, s);
+  int rec_base = option("trsm.rec_base");        // experiments (tools/time_trsm.py): order from which triangles are halved
+  if (rec_base < 2 * NBI) rec_base = REC_BASE;
+  if (nt <= rec_base || (side == 141 ? n : m) < 1024) return trsm_inv_base<T>(side, stored_lower, trans, unit, m, n, A, lda, B, ldb, s);
   const int h = ((nt / 2 + NBI - 1) / NBI) * NBI, r = nt - h;
   const T minus1 = Num<T>::neg(Num<T>::one()), one = Num<T>::one();
   const int eff_lower = (trans == 111) ? stored_lower : !stored_lower;
