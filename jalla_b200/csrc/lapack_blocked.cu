@@ -12,6 +12,18 @@
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
+// Inside the look-ahead loops an error must not `return`: the epilogue joins the second stream into the caller's and
+// frees the scratch.  Sets rc and leaves the loop instead.
+#define JB_CUDA_BREAK(call)                                                                    \
+  {                                                                                            \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess) {                                                                  \
+      jb::set_error(JB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      rc = JB_ERR_CUDA;                                                                        \
+      break;                                                                                   \
+    }                                                                                          \
+  }
+
 namespace jb {
 
 constexpr int NB = 32;           // panel width of the blocked algorithms
@@ -791,8 +803,12 @@ constexpr int CHOL_PANEL_THREADS = 256;
 template <typename T>
 __global__ void __launch_bounds__(CHOL_PANEL_THREADS, 1)
 chol_panel_kernel(int lower, int m, int jb, T *__restrict__ P, int lda, int *info, int off, int *done_count) {
-  __shared__ int s_skip;                                // one read per CTA: info may be set by this very launch
-  if (threadIdx.x == 0) s_skip = *info;
+  // One read per CTA.  info may also be set by CTA 0 of THIS launch (a non-positive pivot in columns off+1 .. off+jb) while
+  // CTAs of a later wave are still starting: such a value must not make them skip — every CTA carries the diagonal block
+  // itself, reaches the same failed_at and parks its partially updated rows like the others, so what A holds for
+  // info > 0 does not depend on scheduling.  Only a failure of an EARLIER panel (info <= off) skips the launch.
+  __shared__ int s_skip;
+  if (threadIdx.x == 0) { const int v = *info; s_skip = (v > off && v <= off + jb) ? 0 : v; }
   __syncthreads();
   if (s_skip) {
     // an earlier panel failed: nothing to do, but the completion count (see the end of the kernel) stays consistent
@@ -1236,8 +1252,8 @@ int getrf_device(int m, int n, T *A, int lda, int *d_ipiv, int *d_info, cudaStre
       if (ahead) {
         rc = right_update(J0, jb2, c0, c0 + jn, s);
         if (rc) break;
-        JB_CUDA(cudaEventRecord(ev_first, s));
-        JB_CUDA(cudaStreamWaitEvent(s2, ev_first, 0));
+        JB_CUDA_BREAK(cudaEventRecord(ev_first, s));
+        JB_CUDA_BREAK(cudaStreamWaitEvent(s2, ev_first, 0));
         tr.mark(s, J0);
         if (J0 > 0) rc = laswp_launch<T>(A, lda, 0, J0, d_ipiv, J0, J0 + jb2, 0, s);
         if (rc) break;
@@ -1265,7 +1281,7 @@ int getrf_device(int m, int n, T *A, int lda, int *d_ipiv, int *d_info, cudaStre
         const int chain_sms = need;
         rc = getrf_mid<T>(m - c0, jn, A + c0 + (size_t)c0 * lda, lda, d_ipiv + c0, d_info, c0, ctx, nbm, s2);
         if (rc) break;
-        JB_CUDA(cudaEventRecord(ev_panel, s2));
+        JB_CUDA_BREAK(cudaEventRecord(ev_panel, s2));
         tr.mark(s2, J0);
         if (overlap) {
           long ncap = (long)(t_chain * rate * (nsm - chain_sms) / flop_col);
@@ -1281,7 +1297,7 @@ int getrf_device(int m, int n, T *A, int lda, int *d_ipiv, int *d_info, cudaStre
           rc = right_update(J0, jb2, cA, n, s);
         }
         tr.mark(s, J0);
-        JB_CUDA(cudaStreamWaitEvent(s, ev_panel, 0));
+        JB_CUDA_BREAK(cudaStreamWaitEvent(s, ev_panel, 0));
         factored = true;
       } else {
         rc = right_update(J0, jb2, c0, n, s);
@@ -1630,8 +1646,8 @@ static int potrf_panels(char uplo, int n, T *A, int lda, int *d_info, int NB2, c
     if (lookahead && c0 + jn < n) {
       rc = update(c0, c0, c0 + jn, J0, c0, s);
       if (rc) break;
-      JB_CUDA(cudaEventRecord(ev_first, s));
-      JB_CUDA(cudaStreamWaitEvent(s2, ev_first, 0));
+      JB_CUDA_BREAK(cudaEventRecord(ev_first, s));
+      JB_CUDA_BREAK(cudaStreamWaitEvent(s2, ev_first, 0));
       tr.mark(s, J0);
       int rsv = option("potrf.reserve_sms");
       const bool timed = option("potrf.timed_cap") != 0;
@@ -1664,7 +1680,7 @@ static int potrf_panels(char uplo, int n, T *A, int lda, int *d_info, int NB2, c
       }
       rc = factor_block(c0, jn, s2, split);      // its skinny updates stay uncapped (waves over the free SMs; capped: 66.3 against 64.2 ms at 16384)
       if (rc) break;
-      JB_CUDA(cudaEventRecord(ev_panel, s2));
+      JB_CUDA_BREAK(cudaEventRecord(ev_panel, s2));
       tr.mark(s2, J0);
       {
         int cs = n;                                      // columns [a0, cs) run capped
@@ -1686,7 +1702,7 @@ static int potrf_panels(char uplo, int n, T *A, int lda, int *d_info, int NB2, c
         if (!rc && cs < n) rc = update(cs, cs, n, J0, c0, s);
       }
       tr.mark(s, J0);
-      JB_CUDA(cudaStreamWaitEvent(s, ev_panel, 0));
+      JB_CUDA_BREAK(cudaStreamWaitEvent(s, ev_panel, 0));
       factored = true;
     } else {
       rc = update(c0, c0, n, J0, c0, s);

@@ -147,31 +147,32 @@ def test_potrf_potrs_batched(orc, rng, t, uplo, n):
         assert fro(X[i] - Bo) <= 1e3 * n * EPS[t] * fro(Bo)
 
 
+@pytest.mark.parametrize("t", "ds")
 @pytest.mark.parametrize("nrhs", [1, 3, 4, 5])
-def test_chol32_tuned_kernels_bit_exact(orc, rng, nrhs):
-    """The tuned Double n = 32 lower-storage Cholesky kernels (csrc/batched_chol32.cu; nrhs <= 4, else the generic solve):
+def test_chol32_tuned_kernels_bit_exact(orc, rng, nrhs, t):
+    """The tuned Double / Float n = 32 lower-storage Cholesky kernels (csrc/batched_chol32.cu; nrhs <= 4, else the generic solve):
     factors bit for bit against the oracle's ?potf2, solutions bit for bit against the generic kernel (same operation
     sequence) and within rounding of the oracle's ?potrs, padded strides between systems,
     the strict upper triangle and the padding untouched, a non-positive pivot and a NaN reported through info."""
     lib.jb_init(-1)
     n, batch = 32, 201
-    M = batch_rand(rng, "d", batch, n)
-    S = np.stack([(m.T @ m + n * np.eye(n)).T for m in M])
+    M = batch_rand(rng, t, batch, n)
+    S = np.stack([(m.T @ m + n * np.eye(n)).T for m in M]).astype(NP[t])
     S[7, 11, 11] = -2.0
     S[9, 4, 4] = np.nan
-    B = batch_rand(rng, "d", batch, n, nrhs)
+    B = batch_rand(rng, t, batch, n, nrhs)
     sa = n * n + 32
-    Sbuf = np.full((batch, sa), np.nan); Sbuf[:, :n * n] = S.reshape(batch, -1)
+    Sbuf = np.full((batch, sa), np.nan, NP[t]); Sbuf[:, :n * n] = S.reshape(batch, -1)
     dS, dB, dI = Dev(Sbuf.copy()), Dev(B.copy()), Dev(np.full(batch, -7, np.int32))
-    check(lib.jb_dpotrf_batched(b"L", n, dS.ptr, n, sa, dI.ptr, batch), "potrf_batched")
-    check(lib.jb_dpotrs_batched(b"L", n, nrhs, dS.ptr, n, sa, dB.ptr, n, n * nrhs, batch), "potrs_batched")
+    check(getattr(lib, f"jb_{t}potrf_batched")(b"L", n, dS.ptr, n, sa, dI.ptr, batch), "potrf_batched")
+    check(getattr(lib, f"jb_{t}potrs_batched")(b"L", n, nrhs, dS.ptr, n, sa, dB.ptr, n, n * nrhs, batch), "potrs_batched")
     check(lib.jb_sync(), "sync")
     F, X, info = dS.get(), dB.get(), dI.get()
     lib.jb_set_option(b"chol32.generic", 1)
     try:
         gS, gB, gI = Dev(Sbuf.copy()), Dev(B.copy()), Dev(np.full(batch, -7, np.int32))
-        check(lib.jb_dpotrf_batched(b"L", n, gS.ptr, n, sa, gI.ptr, batch), "potrf_batched")
-        check(lib.jb_dpotrs_batched(b"L", n, nrhs, gS.ptr, n, sa, gB.ptr, n, n * nrhs, batch), "potrs_batched")
+        check(getattr(lib, f"jb_{t}potrf_batched")(b"L", n, gS.ptr, n, sa, gI.ptr, batch), "potrf_batched")
+        check(getattr(lib, f"jb_{t}potrs_batched")(b"L", n, nrhs, gS.ptr, n, sa, gB.ptr, n, n * nrhs, batch), "potrs_batched")
         check(lib.jb_sync(), "sync")
     finally:
         lib.jb_set_option(b"chol32.generic", -1)
@@ -183,7 +184,7 @@ def test_chol32_tuned_kernels_bit_exact(orc, rng, nrhs):
     up = np.tril_indices(n, -1)
     for i in range(batch):
         So, Bo = S[i].copy(), B[i].copy()
-        io = orc.potrf("d", 102, "L", n, So, n)
+        io = orc.potrf(t, 102, "L", n, So, n)
         if i == 9:
             io = 5        # the batched entry points have no LAPACKE NaN screen: ?potf2 reports the NaN pivot of column 5
         assert info[i] == io, (i, info[i], io)
@@ -192,8 +193,8 @@ def test_chol32_tuned_kernels_bit_exact(orc, rng, nrhs):
         if io:
             continue
         np.testing.assert_array_equal(Fi[low], So[low])
-        orc.potrs("d", 102, "L", n, nrhs, So, n, Bo, n)
-        assert fro(X[i] - Bo) <= 1e3 * n * EPS["d"] * fro(Bo)
+        orc.potrs(t, 102, "L", n, nrhs, So, n, Bo, n)
+        assert fro(X[i] - Bo) <= 1e3 * n * EPS[t] * fro(Bo)
 
 
 @pytest.mark.parametrize("variant", [30, 31, 7, 6, 17, 16])

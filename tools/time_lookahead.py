@@ -22,22 +22,9 @@ def setopts(o, reset=False):
     for k, v in o.items(): lib.jb_set_option(k.encode(), -1 if reset else v)
 
 
-GETRF = [("serial", {"getrf.lookahead": 0}),
-         ("look-ahead (default)", {}),
-         ("look-ahead, round-2b rule (need<=40, 256 rows, whole-update cap)", {"getrf.la_max_need": 40, "getrf.panel_rows": 256, "getrf.la_chain_pct": 100000}),
-         ("look-ahead, nbm 128", {"getrf.nbm": 128}),
-         ("look-ahead, nbm 256", {"getrf.nbm": 256})]
-POTRF = [("serial", {"potrf.lookahead": 0}),
-         ("look-ahead (default: nbm 128, timed cap)", {}),
-         ("look-ahead, round 2b (no middle level, whole-update cap)", {"potrf.nbm": 0, "potrf.timed_cap": 0}),
-         ("look-ahead, nbm 128, whole-update cap", {"potrf.timed_cap": 0}),
-         ("look-ahead, nb2 256", {"potrf.nb2": 256}),
-         ("look-ahead, nb2 512", {"potrf.nb2": 512}),
-         ("look-ahead, nb2 768", {"potrf.nb2": 768}),
-         ("look-ahead, nb2 1024", {"potrf.nb2": 1024}),
-         ("look-ahead, nb2 1024, nbm 256", {"potrf.nb2": 1024, "potrf.nbm": 256}),
-         ("look-ahead, chain 140%", {"potrf.chain_pct": 140}),
-         ("look-ahead, chain 80%", {"potrf.chain_pct": 80})]
+GETRF = [("look-ahead (default)", {})]
+POTRF = [("serial", {"potrf.lookahead": 0}), ("look-ahead (default)", {})] + [("look-ahead, reserve %d, chain %d%%" % (r, c), {"potrf.reserve_sms": r, "potrf.chain_pct": c})
+         for r in (24, 32, 48, 64, 96) for c in (140, 250)]
 for n in [int(x) for x in sys.argv[1:]] or [8192, 16384]:
     A0 = torch.empty(n * n, dtype=torch.float64, device="cuda"); A = torch.empty_like(A0)
     piv = torch.empty(n, dtype=torch.int32, device="cuda")
