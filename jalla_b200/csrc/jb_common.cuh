@@ -214,6 +214,10 @@ template <typename T> int trsm_device(int side, int uplo, int trans, int diag, i
 // the same solve as two GEMMs per 64 rows of the triangle (inverted diagonal blocks; trsm_inv.cu), alpha == 1
 template <typename T> int trsm_inv_device(int side, int stored_lower, int trans, int unit, int m, int n, const T *A, int lda, T *B, int ldb, cudaStream_t s);
 // wide enough for the GEMM form to pay (order of the triangle, number of right-hand sides / rows)
+// the same solve for at most TRSV_MAX_NRHS right-hand sides: one bandwidth-bound launch per 64 rows (trsm_inv.cu)
+constexpr int TRSV_MAX_NRHS = 8;
+template <typename T> int trsv_few_device(int stored_lower, int trans, int unit, int n, int nrhs, const T *A, int lda, T *B, int ldb, cudaStream_t s);
+inline bool trsv_few_pays(int nt, int nrhs) { return nrhs <= TRSV_MAX_NRHS && nt >= 256 && option("trsv.few") != 0; }
 inline bool trsm_inv_pays(int nt, int other) { return nt >= 128 && other >= 256 && option("trsm.inv") != 0; }
 
 }  // namespace jb

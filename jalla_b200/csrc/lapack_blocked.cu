@@ -1331,6 +1331,7 @@ template <typename T>
 static int trsm_left_blocked(int stored_lower, int trans, int unit, int n, int nrhs, const T *A, int lda, T *B, int ldb,
                              cudaStream_t s) {
   if (trsm_inv_pays(n, nrhs)) return trsm_inv_device<T>(141, stored_lower, trans, unit, n, nrhs, A, lda, B, ldb, s);
+  if (trsv_few_pays(n, nrhs)) return trsv_few_device<T>(stored_lower, trans, unit, n, nrhs, A, lda, B, ldb, s);
   const int eff_lower = (trans == 111) ? stored_lower : !stored_lower;
   const int nblk = (n + NB - 1) / NB;
   int blocks = (nrhs + 7) / 8; if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
@@ -1482,7 +1483,9 @@ int getrs_device(char trans, int n, int nrhs, const T *A, int lda, const int *d_
   if (trans == 'N' || trans == 'n') {
     // options: getrs.fused_max_nrhs (unset: 16, 0: never), getrs.fused_max_n (unset: 4096)
     const int fused_nrhs = option("getrs.fused_max_nrhs") >= 0 ? option("getrs.fused_max_nrhs") : 16;
-    const int fused_n = option("getrs.fused_max_n") > 0 ? option("getrs.fused_max_n") : 4096;
+    // measured (tools/time_getrs_few.py, profiles/getrs_few_r2c.jsonl; ms at n = 1024 / 2048 / 4096, one right-hand side):
+    // fused 0.32 / 0.80 / 5.15, bandwidth-bound sweep (trsv_few, <= 8 columns) 0.34 / 0.53 / 0.98, blocked 0.96 / 1.88 / 4.19
+    const int fused_n = option("getrs.fused_max_n") > 0 ? option("getrs.fused_max_n") : (trsv_few_pays(n, nrhs) ? 1024 : 2048);
     if (nrhs <= fused_nrhs && n <= fused_n) {
       const size_t shm = (size_t)n * (sizeof(T) + sizeof(int));
       JB_CUDA(cudaFuncSetAttribute(getrs_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));

@@ -155,7 +155,144 @@ int trsm_inv_device(int side, int stored_lower, int trans, int unit, int m, int 
   return trsm_inv_device<T>(side, stored_lower, trans, unit, m, h, A11, lda, B1, ldb, s);
 }
 
-#define INST(T) template int trsm_inv_device<T>(int, int, int, int, int, int, const T *, int, T *, int, cudaStream_t);
+// ---------------------------------------------------------------------------------------------------------------------
+// A handful of right-hand sides (the Jalla call: solveLinearSystem with a vector, /root/reference/Numeric/Jalla/Matrix.hs:495-508
+// -> ?gesv nrhs = 1; ?getrs / ?potrs likewise).  With one column a triangular solve only STREAMS the triangle once — n^2/2
+// entries, 1 GiB at n = 16384, 0.17 ms at the HBM rate — but the 32-row substitution kernels pay two launches per 32 rows
+// (dgetrs n = 16384, nrhs = 1: 17 ms), and the GEMM-form sweep above has no tile to fill.  Here the same inverted 64 x 64
+// diagonal blocks are used, and one launch per 64 rows does both steps of the sweep:
+//     every CTA:  x_c = op(inv(A_cc)) b_c   (64 x 64, from L2; CTA 0 stores it)      then its rows:  b_r -= op(A)_{r,c} x_c
+// a thread owns a row (NoTrans: coalesced column reads; Trans: 512 contiguous bytes per thread), so the launch is a
+// matrix-vector product at memory speed.  x is collected in a scratch column and copied back at the end: within a launch
+// the other CTAs still read b_c.
+// A CTA of four warps owns 32 rows: warp q multiplies columns 16q .. 16q+15 of the block column (lane = row), and its
+// sixteen loads are issued BEFORE x_c is formed — they do not depend on it — so a launch costs one memory round trip plus
+// the 64 x 64 product (all 128 threads, Dinv from L2, fully unrolled loads) instead of several dependent ones
+// (first version, a thread per row and 64 columns: 18.6 us per launch, dgetrs 16384 x 1 9.5 ms).
+constexpr int TRSV_THREADS = 128, TRSV_ROWS = 32, TRSV_COLS = NBI / 4;
+template <typename T, int NR>
+__global__ void __launch_bounds__(TRSV_THREADS)
+trsv_step_kernel(int trans, int p0, int pb, int rest0, int cnt, const T *__restrict__ A, int lda, const T *__restrict__ Dc,
+                 T *__restrict__ B, int ldb, T *__restrict__ W, int ldw, int nrhs) {
+  __shared__ T bs[NR][NBI], xs[NR][NBI], part[2][NR][NBI], red[4][NR][TRSV_ROWS];
+  const int tid = threadIdx.x, lane = tid & 31, q = tid >> 5;
+  // ---- this thread's sixteen entries of op(A)[row, p0 + 16q ..] (zero outside the block column / the rows)
+  const int r = blockIdx.x * TRSV_ROWS + lane;
+  const bool live = r < cnt;
+  const size_t row = (size_t)rest0 + (live ? r : 0);
+  T a[TRSV_COLS];
+  const int cq = q * TRSV_COLS;
+  if (trans == 111) {
+    const T *Ar = A + row + (size_t)(p0 + cq) * lda;
+#pragma unroll
+    for (int u = 0; u < TRSV_COLS; u++) a[u] = (live && cq + u < pb) ? Ar[(size_t)u * lda] : Num<T>::zero();
+  } else {
+    const T *Ar = A + (p0 + cq) + row * lda;               // op(A)[row, p0 + i] = op(stored A[p0 + i, row])
+#pragma unroll
+    for (int u = 0; u < TRSV_COLS; u++) {
+      T v = (live && cq + u < pb) ? Ar[u] : Num<T>::zero();
+      a[u] = trans == 113 ? Num<T>::conj(v) : v;
+    }
+  }
+  // ---- x_c = op(Dinv_c) b_c: thread (t, h) sums columns 32h .. 32h+31 of row t
+  for (int idx = tid; idx < NR * NBI; idx += TRSV_THREADS) {
+    const int c = idx / NBI, jj = idx % NBI;
+    bs[c][jj] = (c < nrhs && jj < pb) ? B[(size_t)(p0 + jj) + (size_t)c * ldb] : Num<T>::zero();
+  }
+  {
+    const int t = tid & (NBI - 1), h = tid / NBI;
+    T d[NBI / 2];
+#pragma unroll
+    for (int u = 0; u < NBI / 2; u++) {
+      const int jj = h * (NBI / 2) + u;
+      T v = (trans == 111) ? Dc[t + jj * NBI] : Dc[jj + t * NBI];
+      d[u] = trans == 113 ? Num<T>::conj(v) : v;
+    }
+    __syncthreads();
+    T acc[NR];
+#pragma unroll
+    for (int c = 0; c < NR; c++) acc[c] = Num<T>::zero();
+#pragma unroll
+    for (int u = 0; u < NBI / 2; u++)
+#pragma unroll
+      for (int c = 0; c < NR; c++) acc[c] = Num<T>::add(acc[c], Num<T>::mul(d[u], bs[c][h * (NBI / 2) + u]));
+#pragma unroll
+    for (int c = 0; c < NR; c++) part[h][c][t] = acc[c];
+  }
+  __syncthreads();
+  for (int idx = tid; idx < NR * NBI; idx += TRSV_THREADS) {
+    const int c = idx / NBI, t = idx % NBI;
+    const T x = Num<T>::add(part[0][c][t], part[1][c][t]);
+    xs[c][t] = x;
+    if (blockIdx.x == 0 && t < pb && c < nrhs) W[(size_t)(p0 + t) + (size_t)c * ldw] = x;
+  }
+  __syncthreads();
+  if (cnt <= 0) return;
+  // ---- rows: partial products per warp, summed by warp 0
+  {
+    T acc[NR];
+#pragma unroll
+    for (int c = 0; c < NR; c++) acc[c] = Num<T>::zero();
+#pragma unroll
+    for (int u = 0; u < TRSV_COLS; u++)
+#pragma unroll
+      for (int c = 0; c < NR; c++) acc[c] = Num<T>::add(acc[c], Num<T>::mul(a[u], xs[c][cq + u]));
+#pragma unroll
+    for (int c = 0; c < NR; c++) red[q][c][lane] = acc[c];
+  }
+  __syncthreads();
+  if (q == 0 && live) {
+#pragma unroll
+    for (int c = 0; c < NR; c++)
+      if (c < nrhs) {
+        const T sum = Num<T>::add(Num<T>::add(red[0][c][lane], red[1][c][lane]), Num<T>::add(red[2][c][lane], red[3][c][lane]));
+        T *bp = B + row + (size_t)c * ldb;
+        *bp = Num<T>::sub(*bp, sum);
+      }
+  }
+}
+
+// op(Tri) X = B in place, Tri = the stored triangle of A (order n), nrhs <= TRSV_MAX_NRHS.
+template <typename T>
+int trsv_few_device(int stored_lower, int trans, int unit, int n, int nrhs, const T *A, int lda, T *B, int ldb, cudaStream_t s) {
+  if (n <= 0 || nrhs <= 0) return 0;
+  if (nrhs > TRSV_MAX_NRHS) { set_error(JB_ERR_ARG, "trsv_few: too many right-hand sides"); return JB_ERR_ARG; }
+  if (!Num<T>::cplx && trans == 113) trans = 112;
+  const int nblk = (n + NBI - 1) / NBI;
+  T *Dinv = nullptr, *W = nullptr;
+  if (int rc = ws_alloc((void **)&Dinv, sizeof(T) * (size_t)nblk * NBI * NBI, s)) return rc;
+  if (int rc = ws_alloc((void **)&W, sizeof(T) * (size_t)n * nrhs, s)) { ws_free(Dinv, s); return rc; }
+  const int shm = 2 * NBI * NBI_LD * (int)sizeof(T);
+  cudaError_t e = cudaSuccess;
+  if (shm > 48 * 1024) e = cudaFuncSetAttribute(trtri_diag_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, shm);
+  if (e == cudaSuccess) {
+    trtri_diag_kernel<T><<<nblk, 256, shm, s>>>(stored_lower, unit, n, A, lda, Dinv);
+    count_launch();
+  }
+  const int eff_lower = (trans == 111) ? stored_lower : !stored_lower;
+  for (int bi = 0; bi < nblk && e == cudaSuccess; bi++) {
+    const int c = eff_lower ? bi : nblk - 1 - bi;
+    const int p0 = c * NBI, pb = min(NBI, n - p0);
+    const int rest0 = eff_lower ? p0 + pb : 0, cnt = eff_lower ? n - p0 - pb : p0;
+    const int grid = cnt > 0 ? (cnt + TRSV_ROWS - 1) / TRSV_ROWS : 1;
+    const T *Dc = Dinv + (size_t)c * NBI * NBI;
+    if (nrhs == 1) trsv_step_kernel<T, 1><<<grid, TRSV_THREADS, 0, s>>>(trans, p0, pb, rest0, cnt, A, lda, Dc, B, ldb, W, n, nrhs);
+    else if (nrhs == 2) trsv_step_kernel<T, 2><<<grid, TRSV_THREADS, 0, s>>>(trans, p0, pb, rest0, cnt, A, lda, Dc, B, ldb, W, n, nrhs);
+    else if (nrhs <= 4) trsv_step_kernel<T, 4><<<grid, TRSV_THREADS, 0, s>>>(trans, p0, pb, rest0, cnt, A, lda, Dc, B, ldb, W, n, nrhs);
+    else trsv_step_kernel<T, 8><<<grid, TRSV_THREADS, 0, s>>>(trans, p0, pb, rest0, cnt, A, lda, Dc, B, ldb, W, n, nrhs);
+    count_launch();
+  }
+  if (e == cudaSuccess) e = cudaGetLastError();
+  int rc = 0;
+  if (e != cudaSuccess) { set_error(JB_ERR_CUDA, "trsv_few launch failed: %s", cudaGetErrorString(e)); rc = JB_ERR_CUDA; }
+  if (!rc) rc = lacpy_device<T>(111, n, nrhs, W, n, B, ldb, s);
+  ws_free(W, s);
+  ws_free(Dinv, s);
+  return rc;
+}
+
+#define INST(T) template int trsm_inv_device<T>(int, int, int, int, int, int, const T *, int, T *, int, cudaStream_t); \
+  template int trsv_few_device<T>(int, int, int, int, int, const T *, int, T *, int, cudaStream_t);
 INST(float)
 INST(double)
 INST(cfloat)

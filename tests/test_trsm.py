@@ -63,6 +63,24 @@ def test_trsm_gemm_form_all_variants(gpu, blas, rng, t, side, uplo, trans, diag)
     assert np.isnan(Bg[m:]).all()
 
 
+@pytest.mark.parametrize("t", "sdcz")
+@pytest.mark.parametrize("nrhs", [1, 3, 4, 7])
+@pytest.mark.parametrize("uplo,trans,diag", list(itertools.product((121, 122), (111, 112, 113), (131, 132))))
+def test_trsm_few_right_hand_sides(gpu, blas, rng, t, nrhs, uplo, trans, diag):
+    """Left solves of order >= 256 against at most eight right-hand sides take the bandwidth-bound sweep (csrc/trsm_inv.cu,
+    trsv_step_kernel: one launch per 64 rows on the inverted diagonal blocks): ragged last block (300 = 4 x 64 + 44),
+    padded leading dimensions whose NaN padding must survive, every uplo / trans / diag, against OpenBLAS."""
+    m = 300
+    A = tri_matrix(rng, t, m, m + 2)
+    B = rand(rng, t, m, nrhs, m + 3)
+    alpha = 0.5 if t in "sd" else 0.5 - 0.25j
+    Bg, Bb = B.copy(order="F"), B.copy(order="F")
+    gpu.trsm(t, 102, 141, uplo, trans, diag, m, nrhs, alpha, A, m + 2, Bg, m + 3)
+    blas.trsm(t, 102, 141, uplo, trans, diag, m, nrhs, alpha, A, m + 2, Bb, m + 3)
+    assert fro(Bg[:m] - Bb[:m]) / fro(Bb[:m]) <= 200 * m * EPS[t]
+    assert np.isnan(Bg[m:]).all()
+
+
 @pytest.mark.parametrize("t", "dc")
 @pytest.mark.parametrize("side,uplo,trans", list(itertools.product((141, 142), (121, 122), (111, 113))))
 def test_trsm_recursive_halving(gpu, blas, rng, t, side, uplo, trans):
