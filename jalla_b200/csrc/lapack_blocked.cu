@@ -1484,8 +1484,8 @@ int getrs_device(char trans, int n, int nrhs, const T *A, int lda, const int *d_
     // options: getrs.fused_max_nrhs (unset: 16, 0: never), getrs.fused_max_n (unset: 4096)
     const int fused_nrhs = option("getrs.fused_max_nrhs") >= 0 ? option("getrs.fused_max_nrhs") : 16;
     // measured (tools/time_getrs_few.py, profiles/getrs_few_r2c.jsonl; ms at n = 1024 / 2048 / 4096, one right-hand side):
-    // fused 0.32 / 0.80 / 5.15, bandwidth-bound sweep (trsv_few, <= 8 columns) 0.34 / 0.53 / 0.98, blocked 0.96 / 1.88 / 4.19
-    const int fused_n = option("getrs.fused_max_n") > 0 ? option("getrs.fused_max_n") : (trsv_few_pays(n, nrhs) ? 1024 : 2048);
+    // fused 0.32 / 0.80 / 5.15, bandwidth-bound sweep (trsv_few, <= 8 columns) 0.27 / 0.52 / 0.69, blocked 0.96 / 1.88 / 4.19
+    const int fused_n = option("getrs.fused_max_n") > 0 ? option("getrs.fused_max_n") : (trsv_few_pays(n, nrhs) ? 768 : 2048);
     if (nrhs <= fused_nrhs && n <= fused_n) {
       const size_t shm = (size_t)n * (sizeof(T) + sizeof(int));
       JB_CUDA(cudaFuncSetAttribute(getrs_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));

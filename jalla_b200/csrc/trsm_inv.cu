@@ -170,12 +170,16 @@ int trsm_inv_device(int side, int stored_lower, int trans, int unit, int m, int 
 // the 64 x 64 product (all 128 threads, Dinv from L2, fully unrolled loads) instead of several dependent ones
 // (first version, a thread per row and 64 columns: 18.6 us per launch, dgetrs 16384 x 1 9.5 ms).
 constexpr int TRSV_THREADS = 128, TRSV_ROWS = 32, TRSV_COLS = NBI / 4;
+// Launched with programmatic stream serialisation (after the first step): a launch lets its successor start at once, and the
+// successor loads its entries of A and Dinv — which no step writes — while this one is still running, then waits
+// (griddepcontrol.wait = predecessor complete and visible) before it touches B.
 template <typename T, int NR>
 __global__ void __launch_bounds__(TRSV_THREADS)
 trsv_step_kernel(int trans, int p0, int pb, int rest0, int cnt, const T *__restrict__ A, int lda, const T *__restrict__ Dc,
                  T *__restrict__ B, int ldb, T *__restrict__ W, int ldw, int nrhs) {
   __shared__ T bs[NR][NBI], xs[NR][NBI], part[2][NR][NBI], red[4][NR][TRSV_ROWS];
   const int tid = threadIdx.x, lane = tid & 31, q = tid >> 5;
+  asm volatile("griddepcontrol.launch_dependents;");
   // ---- this thread's sixteen entries of op(A)[row, p0 + 16q ..] (zero outside the block column / the rows)
   const int r = blockIdx.x * TRSV_ROWS + lane;
   const bool live = r < cnt;
@@ -195,10 +199,6 @@ trsv_step_kernel(int trans, int p0, int pb, int rest0, int cnt, const T *__restr
     }
   }
   // ---- x_c = op(Dinv_c) b_c: thread (t, h) sums columns 32h .. 32h+31 of row t
-  for (int idx = tid; idx < NR * NBI; idx += TRSV_THREADS) {
-    const int c = idx / NBI, jj = idx % NBI;
-    bs[c][jj] = (c < nrhs && jj < pb) ? B[(size_t)(p0 + jj) + (size_t)c * ldb] : Num<T>::zero();
-  }
   {
     const int t = tid & (NBI - 1), h = tid / NBI;
     T d[NBI / 2];
@@ -207,6 +207,11 @@ trsv_step_kernel(int trans, int p0, int pb, int rest0, int cnt, const T *__restr
       const int jj = h * (NBI / 2) + u;
       T v = (trans == 111) ? Dc[t + jj * NBI] : Dc[jj + t * NBI];
       d[u] = trans == 113 ? Num<T>::conj(v) : v;
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");          // B as the previous step left it
+    for (int idx = tid; idx < NR * NBI; idx += TRSV_THREADS) {
+      const int c = idx / NBI, jj = idx % NBI;
+      bs[c][jj] = (c < nrhs && jj < pb) ? B[(size_t)(p0 + jj) + (size_t)c * ldb] : Num<T>::zero();
     }
     __syncthreads();
     T acc[NR];
@@ -270,16 +275,24 @@ int trsv_few_device(int stored_lower, int trans, int unit, int n, int nrhs, cons
     count_launch();
   }
   const int eff_lower = (trans == 111) ? stored_lower : !stored_lower;
+  const bool pdl = option("trsv.pdl") != 0;
   for (int bi = 0; bi < nblk && e == cudaSuccess; bi++) {
     const int c = eff_lower ? bi : nblk - 1 - bi;
     const int p0 = c * NBI, pb = min(NBI, n - p0);
     const int rest0 = eff_lower ? p0 + pb : 0, cnt = eff_lower ? n - p0 - pb : p0;
     const int grid = cnt > 0 ? (cnt + TRSV_ROWS - 1) / TRSV_ROWS : 1;
     const T *Dc = Dinv + (size_t)c * NBI * NBI;
-    if (nrhs == 1) trsv_step_kernel<T, 1><<<grid, TRSV_THREADS, 0, s>>>(trans, p0, pb, rest0, cnt, A, lda, Dc, B, ldb, W, n, nrhs);
-    else if (nrhs == 2) trsv_step_kernel<T, 2><<<grid, TRSV_THREADS, 0, s>>>(trans, p0, pb, rest0, cnt, A, lda, Dc, B, ldb, W, n, nrhs);
-    else if (nrhs <= 4) trsv_step_kernel<T, 4><<<grid, TRSV_THREADS, 0, s>>>(trans, p0, pb, rest0, cnt, A, lda, Dc, B, ldb, W, n, nrhs);
-    else trsv_step_kernel<T, 8><<<grid, TRSV_THREADS, 0, s>>>(trans, p0, pb, rest0, cnt, A, lda, Dc, B, ldb, W, n, nrhs);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TRSV_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = (bi > 0 && pdl) ? 1 : 0;        // the first step follows trtri_diag in plain stream order
+    T *Bp = B, *Wp = W;
+    if (nrhs == 1) e = cudaLaunchKernelEx(&cfg, trsv_step_kernel<T, 1>, trans, p0, pb, rest0, cnt, A, lda, Dc, Bp, ldb, Wp, n, nrhs);
+    else if (nrhs == 2) e = cudaLaunchKernelEx(&cfg, trsv_step_kernel<T, 2>, trans, p0, pb, rest0, cnt, A, lda, Dc, Bp, ldb, Wp, n, nrhs);
+    else if (nrhs <= 4) e = cudaLaunchKernelEx(&cfg, trsv_step_kernel<T, 4>, trans, p0, pb, rest0, cnt, A, lda, Dc, Bp, ldb, Wp, n, nrhs);
+    else e = cudaLaunchKernelEx(&cfg, trsv_step_kernel<T, 8>, trans, p0, pb, rest0, cnt, A, lda, Dc, Bp, ldb, Wp, n, nrhs);
     count_launch();
   }
   if (e == cudaSuccess) e = cudaGetLastError();

@@ -22,7 +22,7 @@ for n in [int(x) for x in sys.argv[1:]] or [1024, 2048, 4096, 8192, 16384]:
         b0 = torch.empty(n * nrhs, dtype=torch.float64, device="cuda"); check(lib.jb_dfill_uniform(b0.data_ptr(), n, n, nrhs, 0, 0, 5, 0, 0.0), "fill")
         b = torch.empty_like(b0)
         tc = ev(lambda: b.copy_(b0))
-        for name, opts in (("sweep", {"getrs.fused_max_n": 1}), ("fused (n <= 4096)", {"trsv.few": 0}), ("blocked", {"trsv.few": 0, "getrs.fused_max_n": 1}), ("default", {})):
+        for name, opts in (("sweep", {"getrs.fused_max_n": 1}), ("sweep, plain launches", {"getrs.fused_max_n": 1, "trsv.pdl": 0}), ("fused (n <= 4096)", {"trsv.few": 0}), ("blocked", {"trsv.few": 0, "getrs.fused_max_n": 1}), ("default", {})):
             if name.startswith("fused") and n > 4096: continue
             for k, v in opts.items(): lib.jb_set_option(k.encode(), v)
             def run(): b.copy_(b0); assert lib.LAPACKE_dgetrs(102, b"N", n, nrhs, A.data_ptr(), n, piv.data_ptr(), b.data_ptr(), n) == 0
