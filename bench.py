@@ -241,7 +241,7 @@ def verify_columns(np, torch, gemm, ncols):
     return err, bound
 
 
-def factorisations(torch, lib, check, stream):
+def factorisations(torch, lib, check, stream, hbm_gbs):
     """Large single-GPU LAPACKE calls on device-resident Double data (CUDA events around the call, copies subtracted):
     dgetrf / dpotrf / dgesv (nrhs = 1, the Jalla call) at 8192 and 16384, as fractions of the measured DMMA peak."""
     out = {}
@@ -268,6 +268,12 @@ def factorisations(torch, lib, check, stream):
         def gesv():
             A.copy_(A0); b.copy_(b0); assert lib.LAPACKE_dgesv(102, n, 1, A.data_ptr(), n, piv.data_ptr(), b.data_ptr(), n) == 0
         t_getrf, t_gesv = ev(getrf) - t_copy, ev(gesv) - t_copy
+        # the solve alone on the factors gesv left in A (one right-hand side: the bandwidth-bound sweep of csrc/trsm_inv.cu)
+        t_bcopy = ev(lambda: b.copy_(b0), reps=5)
+
+        def getrs():
+            b.copy_(b0); assert lib.LAPACKE_dgetrs(102, b"N", n, 1, A.data_ptr(), n, piv.data_ptr(), b.data_ptr(), n) == 0
+        t_getrs = ev(getrs, reps=5) - t_bcopy
         check(lib.jb_dfill_uniform(A0.data_ptr(), n, n, n, 0, 0, SEED + 3, 1, float(n)), "fill spd")
 
         def potrf():
@@ -275,7 +281,8 @@ def factorisations(torch, lib, check, stream):
         t_potrf = ev(potrf) - t_copy
         f_lu, f_ch = 2.0 / 3.0 * n ** 3, n ** 3 / 3.0
         out[f"n{n}"] = {"dgetrf_ms": t_getrf, "dgetrf_tflops": f_lu / t_getrf / 1e9, "dgetrf_frac_of_dmma_peak": f_lu / t_getrf / 1e9 / DMMA_PEAK_TFLOPS,
-                        "dgesv_nrhs1_ms": t_gesv, "dpotrf_ms": t_potrf, "dpotrf_tflops": f_ch / t_potrf / 1e9,
+                        "dgesv_nrhs1_ms": t_gesv, "dgetrs_nrhs1_ms": t_getrs, "dgetrs_nrhs1_frac_of_hbm": n * n * 8.0 / t_getrs / 1e6 / hbm_gbs,
+                        "dpotrf_ms": t_potrf, "dpotrf_tflops": f_ch / t_potrf / 1e9,
                         "dpotrf_frac_of_dmma_peak": f_ch / t_potrf / 1e9 / DMMA_PEAK_TFLOPS}
         if n == 8192:
             # invert (Matrix.hs:537-540: getrf + getri) and the level-3 triangular solve both run on the GEMM-form trsm
@@ -586,7 +593,7 @@ def main():
         del lu2
         torch.cuda.empty_cache()
     if world == 1 and args.only == "" and not args.no_other:
-        out["factorisations"] = factorisations(torch, lib, check, stream)
+        out["factorisations"] = factorisations(torch, lib, check, stream, measured_peaks()[0])
         out["batched_cholesky"] = batched_cholesky(torch, lib, check, stream, measured_peaks()[0])
     if world == 8 and args.only == "" and not args.no_other:
         gemm.close()

@@ -84,6 +84,7 @@ static int gemm_host_pipelined(int ta, int tb, int m, int n, int k, T alpha, con
   T *dA = nullptr, *dB = nullptr, *dC = nullptr;
   cudaEvent_t ev_start = nullptr, ev_tile = nullptr;
   cudaEvent_t *ev_a = nullptr, *ev_b = nullptr;
+  cudaEvent_t ev_k[4] = {nullptr, nullptr, nullptr, nullptr};
   int rc = 0;
   cudaError_t e = cudaSuccess;
 #define PL_CUDA(x) do { e = (x); if (e != cudaSuccess) { set_error(JB_ERR_CUDA, "gemm (host pipeline): %s", cudaGetErrorString(e)); rc = JB_ERR_CUDA; goto done; } } while (0)
@@ -96,6 +97,7 @@ static int gemm_host_pipelined(int ta, int tb, int m, int n, int k, T alpha, con
   if ((rc = ws_alloc((void **)&dC, (size_t)lddc * n * sizeof(T), s))) goto done;
   for (int i = 0; i < nblocks; i++) PL_CUDA(cudaEventCreateWithFlags(&ev_a[i], cudaEventDisableTiming));
   for (int j = 0; j < npanels; j++) PL_CUDA(cudaEventCreateWithFlags(&ev_b[j], cudaEventDisableTiming));
+  for (int c = 0; c < 4; c++) PL_CUDA(cudaEventCreateWithFlags(&ev_k[c], cudaEventDisableTiming));
   PL_CUDA(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
   PL_CUDA(cudaEventCreateWithFlags(&ev_tile, cudaEventDisableTiming));
   PL_CUDA(cudaEventRecord(ev_start, s));                       // buffers come from s's pool: order the side streams after it
@@ -118,20 +120,49 @@ static int gemm_host_pipelined(int ta, int tb, int m, int n, int k, T alpha, con
       else ce = cudaMemcpy2DAsync(dB + c0, (size_t)lddb * sizeof(T), B + c0, (size_t)ldb * sizeof(T), (size_t)nc * sizeof(T), (size_t)k, cudaMemcpyHostToDevice, sin);
       return ce == cudaSuccess ? cudaEventRecord(ev_b[j], sin) : ce;
     };
-    PL_CUDA(copy_a(0));
-    PL_CUDA(copy_b(0));
+    // The first tile would wait for ALL of A block 0 and B panel 0 (1.25 GiB at N = 16384: 24 ms of a 270 ms call).  Its
+    // operands therefore arrive in NKC slices along K, and the tile is accumulated slice by slice (beta, then 1) as they
+    // land: the first product starts after 1/NKC of that wait.
+    const int NKC = (k >= 8192 && option("gemm.e2e_kchunks") != 0) ? 4 : 1;
+    const int KC = ((k + NKC - 1) / NKC + 15) / 16 * 16;
+    {
+      const int mr0 = (m < MB) ? m : MB, nc0 = (n < NP) ? n : NP;
+      if (!beta0) PL_CUDA(cudaMemcpy2DAsync(dC, (size_t)lddc * sizeof(T), C, (size_t)ldc * sizeof(T), (size_t)mr0 * sizeof(T), (size_t)n, cudaMemcpyHostToDevice, sin));
+      for (int c = 0; c < NKC; c++) {
+        const int k0 = c * KC, kc = (k - k0 < KC) ? (k - k0) : KC;
+        if (kc <= 0) break;
+        if (ta == 111) PL_CUDA(cudaMemcpy2DAsync(dA + (size_t)k0 * ldda, (size_t)ldda * sizeof(T), A + (size_t)k0 * lda, (size_t)lda * sizeof(T), (size_t)mr0 * sizeof(T), (size_t)kc, cudaMemcpyHostToDevice, sin));
+        else PL_CUDA(cudaMemcpy2DAsync(dA + k0, (size_t)ldda * sizeof(T), A + k0, (size_t)lda * sizeof(T), (size_t)kc * sizeof(T), (size_t)mr0, cudaMemcpyHostToDevice, sin));
+        if (tb == 111) PL_CUDA(cudaMemcpy2DAsync(dB + k0, (size_t)lddb * sizeof(T), B + k0, (size_t)ldb * sizeof(T), (size_t)kc * sizeof(T), (size_t)nc0, cudaMemcpyHostToDevice, sin));
+        else PL_CUDA(cudaMemcpy2DAsync(dB + (size_t)k0 * lddb, (size_t)lddb * sizeof(T), B + (size_t)k0 * ldb, (size_t)ldb * sizeof(T), (size_t)nc0 * sizeof(T), (size_t)kc, cudaMemcpyHostToDevice, sin));
+        PL_CUDA(cudaEventRecord(ev_k[c], sin));
+      }
+      PL_CUDA(cudaEventRecord(ev_a[0], sin));
+      PL_CUDA(cudaEventRecord(ev_b[0], sin));
+    }
     for (int j = 1; j < npanels; j++) PL_CUDA(copy_b(j));
     for (int i = 1; i < nblocks; i++) PL_CUDA(copy_a(i));
     for (int i = 0; i < nblocks; i++) {
       const int r0 = i * MB, mr = (m - r0 < MB) ? (m - r0) : MB;
-      PL_CUDA(cudaStreamWaitEvent(s, ev_a[i], 0));
+      if (i > 0) PL_CUDA(cudaStreamWaitEvent(s, ev_a[i], 0));
       for (int j = 0; j < npanels; j++) {
         const int c0 = j * NP, nc = (n - c0 < NP) ? (n - c0) : NP;
-        if (i == 0) PL_CUDA(cudaStreamWaitEvent(s, ev_b[j], 0));
+        if (i == 0 && j > 0) PL_CUDA(cudaStreamWaitEvent(s, ev_b[j], 0));
         const T *pa = (ta == 111) ? dA + r0 : dA + (size_t)r0 * ldda;
         const T *pb = (tb == 111) ? dB + (size_t)c0 * lddb : dB + c0;
         T *pc = dC + r0 + (size_t)c0 * lddc;
-        rc = gemm_device<T>(ta, tb, mr, nc, k, alpha, pa, ldda, pb, lddb, beta, pc, lddc, s, 0);
+        if (i == 0 && j == 0) {
+          for (int c = 0; c < NKC && !rc; c++) {
+            const int k0 = c * KC, kc = (k - k0 < KC) ? (k - k0) : KC;
+            if (kc <= 0) break;
+            PL_CUDA(cudaStreamWaitEvent(s, ev_k[c], 0));
+            const T *pak = (ta == 111) ? pa + (size_t)k0 * ldda : pa + k0;
+            const T *pbk = (tb == 111) ? pb + k0 : pb + (size_t)k0 * lddb;
+            rc = gemm_device<T>(ta, tb, mr, nc, kc, alpha, pak, ldda, pbk, lddb, c == 0 ? beta : Num<T>::one(), pc, lddc, s, 0);
+          }
+        } else {
+          rc = gemm_device<T>(ta, tb, mr, nc, k, alpha, pa, ldda, pb, lddb, beta, pc, lddc, s, 0);
+        }
         if (rc) goto done;
         PL_CUDA(cudaEventRecord(ev_tile, s));
         PL_CUDA(cudaStreamWaitEvent(sout, ev_tile, 0));
@@ -149,6 +180,7 @@ done:
   cudaStreamSynchronize(s);
   if (ev_a) { for (int i = 0; i < nblocks; i++) if (ev_a[i]) cudaEventDestroy(ev_a[i]); delete[] ev_a; }
   if (ev_b) { for (int j = 0; j < npanels; j++) if (ev_b[j]) cudaEventDestroy(ev_b[j]); delete[] ev_b; }
+  for (int c = 0; c < 4; c++) if (ev_k[c]) cudaEventDestroy(ev_k[c]);
   if (ev_start) cudaEventDestroy(ev_start);
   if (ev_tile) cudaEventDestroy(ev_tile);
   ws_free(dC, s); ws_free(dB, s); ws_free(dA, s);
