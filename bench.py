@@ -580,12 +580,16 @@ def main():
             n = N_GEMM
             Ah = np.empty((n, n), order="F"); Bh = np.empty((n, n), order="F"); Ch = np.empty((n, n), order="F")
             check(lib.jb_memcpy_d2h(Ah.ctypes.data, gemm.A_ptr, Ah.nbytes), "d2h"); check(lib.jb_memcpy_d2h(Bh.ctypes.data, gemm.B_ptr, Bh.nbytes), "d2h")
-            t0 = time.perf_counter()
-            lib.cblas_dgemm(102, 111, 111, n, n, n, 1.0, Ah.ctypes.data, n, Bh.ctypes.data, n, 0.0, Ch.ctypes.data, n)
-            dt = time.perf_counter() - t0
-            check_last("pageable e2e")
-            out["e2e"]["pageable_host"] = {"value": 2.0 * n ** 3 / dt / 1e12, "unit": "TFLOP/s", "ms_per_step": dt * 1e3,
-                                           "path": "cblas_dgemm(pageable numpy A,B,C), one call"}
+            dts = []
+            for _ in range(2):       # the first call also allocates the library's pinned staging slots and starts its copy threads
+                Ch = np.empty((n, n), order="F")          # fresh untouched pages, as matrixAlloc' hands them to matrixMult
+                t0 = time.perf_counter()
+                lib.cblas_dgemm(102, 111, 111, n, n, n, 1.0, Ah.ctypes.data, n, Bh.ctypes.data, n, 0.0, Ch.ctypes.data, n)
+                dts.append(time.perf_counter() - t0)
+                check_last("pageable e2e")
+            dt = dts[1]
+            out["e2e"]["pageable_host"] = {"value": 2.0 * n ** 3 / dt / 1e12, "unit": "TFLOP/s", "ms_per_step": dt * 1e3, "first_call_ms": dts[0] * 1e3,
+                                           "path": "cblas_dgemm(pageable numpy A,B,C): the library's own staging through pinned slots filled by host threads (csrc/host_stage.cu)"}
             del Ah, Bh, Ch
     if "lu" in res and not args.no_e2e and "batched_lu" in out:
         lu2 = jdist.ShardedBatchedLU(grid, LU_N, LU_BATCH, seed=SEED)

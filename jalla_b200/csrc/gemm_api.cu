@@ -68,10 +68,12 @@ static void gemm_entry(const char *name, int order, int ta, int tb, int m, int n
 template <typename T>
 static int gemm_host_pipelined(int ta, int tb, int m, int n, int k, T alpha, const T *A, int lda, const T *B, int ldb,
                                T beta, T *C, int ldc, cudaStream_t s) {
-  // C is cut into R row blocks x P column panels.  Copy order on the H2D stream: A block 0, B panel 0, the other B
-  // panels, then the other A blocks; tile (i,j) starts as soon as A block i and B panel j have landed, and its
-  // result leaves on the D2H stream while the next tile multiplies.  PCIe moves the operands (2 x N^2) faster than
-  // the GEMM consumes them, so after the first tile's operands the copies hide completely under the kernel.
+  // C is cut into R row blocks x P column panels.  Issue order (copies on the H2D stream, products on the call's stream,
+  // results on the D2H stream): A block 0 and B panel 0, tile (0,0); then panel j, tile (0,j) for the other panels; then
+  // block i, tiles (i, *).  A tile waits only for its own operands and its result leaves while the next one multiplies;
+  // PCIe moves the operands (2 x N^2) faster than the GEMM consumes them, so after the first tile the copies hide under
+  // the kernel.  Copies and products are issued interleaved because a copy from PAGEABLE memory blocks the caller while
+  // the host threads fill a pinned slot (HostStage) — the device must already hold the work that overlaps it.
   const bool beta0 = Num<T>::is_zero(beta);
   const int R = (m >= 8192) ? 2 : 1;
   const int MB = ((m + R - 1) / R + 127) / 128 * 128;          // rows of op(A)/C per block
@@ -80,109 +82,89 @@ static int gemm_host_pipelined(int ta, int tb, int m, int n, int k, T alpha, con
   const long ra = (ta == 111) ? m : k, ca = (ta == 111) ? k : m;
   const long rb = (tb == 111) ? k : n, cb = (tb == 111) ? n : k;
   const int ldda = (int)(ra + (ra & 1)), lddb = (int)(rb + (rb & 1)), lddc = m + (m & 1);
+  const size_t E = sizeof(T);
   cudaStream_t sin = nullptr, sout = nullptr;
   T *dA = nullptr, *dB = nullptr, *dC = nullptr;
-  cudaEvent_t ev_start = nullptr, ev_tile = nullptr;
-  cudaEvent_t *ev_a = nullptr, *ev_b = nullptr;
-  cudaEvent_t ev_k[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_start = nullptr, ev_tile = nullptr, ev_in = nullptr;
+  HostStage stage;
   int rc = 0;
   cudaError_t e = cudaSuccess;
 #define PL_CUDA(x) do { e = (x); if (e != cudaSuccess) { set_error(JB_ERR_CUDA, "gemm (host pipeline): %s", cudaGetErrorString(e)); rc = JB_ERR_CUDA; goto done; } } while (0)
-  ev_a = new cudaEvent_t[nblocks]();
-  ev_b = new cudaEvent_t[npanels]();
+#define PL_RC(x) do { rc = (x); if (rc) goto done; } while (0)
   PL_CUDA(cudaStreamCreateWithFlags(&sin, cudaStreamNonBlocking));
   PL_CUDA(cudaStreamCreateWithFlags(&sout, cudaStreamNonBlocking));
-  if ((rc = ws_alloc((void **)&dA, (size_t)ldda * ca * sizeof(T), s))) goto done;
-  if ((rc = ws_alloc((void **)&dB, (size_t)lddb * cb * sizeof(T), s))) goto done;
-  if ((rc = ws_alloc((void **)&dC, (size_t)lddc * n * sizeof(T), s))) goto done;
-  for (int i = 0; i < nblocks; i++) PL_CUDA(cudaEventCreateWithFlags(&ev_a[i], cudaEventDisableTiming));
-  for (int j = 0; j < npanels; j++) PL_CUDA(cudaEventCreateWithFlags(&ev_b[j], cudaEventDisableTiming));
-  for (int c = 0; c < 4; c++) PL_CUDA(cudaEventCreateWithFlags(&ev_k[c], cudaEventDisableTiming));
+  if ((rc = ws_alloc((void **)&dA, (size_t)ldda * ca * E, s))) goto done;
+  if ((rc = ws_alloc((void **)&dB, (size_t)lddb * cb * E, s))) goto done;
+  if ((rc = ws_alloc((void **)&dC, (size_t)lddc * n * E, s))) goto done;
   PL_CUDA(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
   PL_CUDA(cudaEventCreateWithFlags(&ev_tile, cudaEventDisableTiming));
+  PL_CUDA(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
   PL_CUDA(cudaEventRecord(ev_start, s));                       // buffers come from s's pool: order the side streams after it
   PL_CUDA(cudaStreamWaitEvent(sin, ev_start, 0));
   PL_CUDA(cudaStreamWaitEvent(sout, ev_start, 0));
   {
-    auto copy_a = [&](int i) -> cudaError_t {                  // rows [i*MB, ..) of op(A)
-      const int r0 = i * MB, mr = (m - r0 < MB) ? (m - r0) : MB;
-      cudaError_t ce;
-      if (ta == 111) ce = cudaMemcpy2DAsync(dA + r0, (size_t)ldda * sizeof(T), A + r0, (size_t)lda * sizeof(T), (size_t)mr * sizeof(T), (size_t)k, cudaMemcpyHostToDevice, sin);
-      else ce = cudaMemcpy2DAsync(dA + (size_t)r0 * ldda, (size_t)ldda * sizeof(T), A + (size_t)r0 * lda, (size_t)lda * sizeof(T), (size_t)k * sizeof(T), (size_t)mr, cudaMemcpyHostToDevice, sin);
-      if (ce == cudaSuccess && !beta0)
-        ce = cudaMemcpy2DAsync(dC + r0, (size_t)lddc * sizeof(T), C + r0, (size_t)ldc * sizeof(T), (size_t)mr * sizeof(T), (size_t)n, cudaMemcpyHostToDevice, sin);
-      return ce == cudaSuccess ? cudaEventRecord(ev_a[i], sin) : ce;
+    // rows [r0, r0 + mr) of op(A), inner indices [k0, k0 + kc)
+    auto copy_a = [&](int r0, int mr, int k0, int kc) -> int {
+      if (ta == 111) return stage.h2d(dA + r0 + (size_t)k0 * ldda, (size_t)ldda * E, A + r0 + (size_t)k0 * lda, (size_t)lda * E, (size_t)mr * E, (size_t)kc, sin);
+      return stage.h2d(dA + k0 + (size_t)r0 * ldda, (size_t)ldda * E, A + k0 + (size_t)r0 * lda, (size_t)lda * E, (size_t)kc * E, (size_t)mr, sin);
     };
-    auto copy_b = [&](int j) -> cudaError_t {                  // columns [j*NP, ..) of op(B)
-      const int c0 = j * NP, nc = (n - c0 < NP) ? (n - c0) : NP;
-      cudaError_t ce;
-      if (tb == 111) ce = cudaMemcpy2DAsync(dB + (size_t)c0 * lddb, (size_t)lddb * sizeof(T), B + (size_t)c0 * ldb, (size_t)ldb * sizeof(T), (size_t)k * sizeof(T), (size_t)nc, cudaMemcpyHostToDevice, sin);
-      else ce = cudaMemcpy2DAsync(dB + c0, (size_t)lddb * sizeof(T), B + c0, (size_t)ldb * sizeof(T), (size_t)nc * sizeof(T), (size_t)k, cudaMemcpyHostToDevice, sin);
-      return ce == cudaSuccess ? cudaEventRecord(ev_b[j], sin) : ce;
+    // columns [c0, c0 + nc) of op(B), inner indices [k0, k0 + kc)
+    auto copy_b = [&](int c0, int nc, int k0, int kc) -> int {
+      if (tb == 111) return stage.h2d(dB + k0 + (size_t)c0 * lddb, (size_t)lddb * E, B + k0 + (size_t)c0 * ldb, (size_t)ldb * E, (size_t)kc * E, (size_t)nc, sin);
+      return stage.h2d(dB + c0 + (size_t)k0 * lddb, (size_t)lddb * E, B + c0 + (size_t)k0 * ldb, (size_t)ldb * E, (size_t)nc * E, (size_t)kc, sin);
+    };
+    auto landed = [&]() -> cudaError_t {                       // the call's stream waits for everything queued on sin so far
+      cudaError_t ce = cudaEventRecord(ev_in, sin);
+      return ce == cudaSuccess ? cudaStreamWaitEvent(s, ev_in, 0) : ce;
     };
     // The first tile would wait for ALL of A block 0 and B panel 0 (1.25 GiB at N = 16384: 24 ms of a 270 ms call).  Its
     // operands therefore arrive in NKC slices along K, and the tile is accumulated slice by slice (beta, then 1) as they
     // land: the first product starts after 1/NKC of that wait.
     const int NKC = (k >= 8192 && option("gemm.e2e_kchunks") != 0) ? 4 : 1;
     const int KC = ((k + NKC - 1) / NKC + 15) / 16 * 16;
-    {
-      const int mr0 = (m < MB) ? m : MB, nc0 = (n < NP) ? n : NP;
-      if (!beta0) PL_CUDA(cudaMemcpy2DAsync(dC, (size_t)lddc * sizeof(T), C, (size_t)ldc * sizeof(T), (size_t)mr0 * sizeof(T), (size_t)n, cudaMemcpyHostToDevice, sin));
-      for (int c = 0; c < NKC; c++) {
-        const int k0 = c * KC, kc = (k - k0 < KC) ? (k - k0) : KC;
-        if (kc <= 0) break;
-        if (ta == 111) PL_CUDA(cudaMemcpy2DAsync(dA + (size_t)k0 * ldda, (size_t)ldda * sizeof(T), A + (size_t)k0 * lda, (size_t)lda * sizeof(T), (size_t)mr0 * sizeof(T), (size_t)kc, cudaMemcpyHostToDevice, sin));
-        else PL_CUDA(cudaMemcpy2DAsync(dA + k0, (size_t)ldda * sizeof(T), A + k0, (size_t)lda * sizeof(T), (size_t)kc * sizeof(T), (size_t)mr0, cudaMemcpyHostToDevice, sin));
-        if (tb == 111) PL_CUDA(cudaMemcpy2DAsync(dB + k0, (size_t)lddb * sizeof(T), B + k0, (size_t)ldb * sizeof(T), (size_t)kc * sizeof(T), (size_t)nc0, cudaMemcpyHostToDevice, sin));
-        else PL_CUDA(cudaMemcpy2DAsync(dB + (size_t)k0 * lddb, (size_t)lddb * sizeof(T), B + (size_t)k0 * ldb, (size_t)ldb * sizeof(T), (size_t)nc0 * sizeof(T), (size_t)kc, cudaMemcpyHostToDevice, sin));
-        PL_CUDA(cudaEventRecord(ev_k[c], sin));
-      }
-      PL_CUDA(cudaEventRecord(ev_a[0], sin));
-      PL_CUDA(cudaEventRecord(ev_b[0], sin));
-    }
-    for (int j = 1; j < npanels; j++) PL_CUDA(copy_b(j));
-    for (int i = 1; i < nblocks; i++) PL_CUDA(copy_a(i));
     for (int i = 0; i < nblocks; i++) {
       const int r0 = i * MB, mr = (m - r0 < MB) ? (m - r0) : MB;
-      if (i > 0) PL_CUDA(cudaStreamWaitEvent(s, ev_a[i], 0));
+      if (!beta0) PL_RC(stage.h2d(dC + r0, (size_t)lddc * E, C + r0, (size_t)ldc * E, (size_t)mr * E, (size_t)n, sin));
+      if (i > 0) { PL_RC(copy_a(r0, mr, 0, k)); PL_CUDA(landed()); }
       for (int j = 0; j < npanels; j++) {
         const int c0 = j * NP, nc = (n - c0 < NP) ? (n - c0) : NP;
-        if (i == 0 && j > 0) PL_CUDA(cudaStreamWaitEvent(s, ev_b[j], 0));
         const T *pa = (ta == 111) ? dA + r0 : dA + (size_t)r0 * ldda;
         const T *pb = (tb == 111) ? dB + (size_t)c0 * lddb : dB + c0;
         T *pc = dC + r0 + (size_t)c0 * lddc;
         if (i == 0 && j == 0) {
-          for (int c = 0; c < NKC && !rc; c++) {
+          for (int c = 0; c < NKC; c++) {
             const int k0 = c * KC, kc = (k - k0 < KC) ? (k - k0) : KC;
             if (kc <= 0) break;
-            PL_CUDA(cudaStreamWaitEvent(s, ev_k[c], 0));
+            PL_RC(copy_a(r0, mr, k0, kc));
+            PL_RC(copy_b(c0, nc, k0, kc));
+            PL_CUDA(landed());
             const T *pak = (ta == 111) ? pa + (size_t)k0 * ldda : pa + k0;
             const T *pbk = (tb == 111) ? pb + k0 : pb + (size_t)k0 * lddb;
-            rc = gemm_device<T>(ta, tb, mr, nc, kc, alpha, pak, ldda, pbk, lddb, c == 0 ? beta : Num<T>::one(), pc, lddc, s, 0);
+            PL_RC(gemm_device<T>(ta, tb, mr, nc, kc, alpha, pak, ldda, pbk, lddb, c == 0 ? beta : Num<T>::one(), pc, lddc, s, 0));
           }
         } else {
-          rc = gemm_device<T>(ta, tb, mr, nc, k, alpha, pa, ldda, pb, lddb, beta, pc, lddc, s, 0);
+          if (i == 0) { PL_RC(copy_b(c0, nc, 0, k)); PL_CUDA(landed()); }
+          PL_RC(gemm_device<T>(ta, tb, mr, nc, k, alpha, pa, ldda, pb, lddb, beta, pc, lddc, s, 0));
         }
-        if (rc) goto done;
         PL_CUDA(cudaEventRecord(ev_tile, s));
         PL_CUDA(cudaStreamWaitEvent(sout, ev_tile, 0));
-        PL_CUDA(cudaMemcpy2DAsync(C + r0 + (size_t)c0 * ldc, (size_t)ldc * sizeof(T), pc, (size_t)lddc * sizeof(T),
-                                  (size_t)mr * sizeof(T), (size_t)nc, cudaMemcpyDeviceToHost, sout));
+        PL_RC(stage.d2h(C + r0 + (size_t)c0 * ldc, (size_t)ldc * E, pc, (size_t)lddc * E, (size_t)mr * E, (size_t)nc, sout));
       }
     }
   }
+  PL_RC(stage.finish());
   PL_CUDA(cudaStreamSynchronize(sout));
   PL_CUDA(cudaStreamSynchronize(s));
 done:
 #undef PL_CUDA
+#undef PL_RC
+  stage.finish();
   if (sin) cudaStreamSynchronize(sin);
   if (sout) cudaStreamSynchronize(sout);
   cudaStreamSynchronize(s);
-  if (ev_a) { for (int i = 0; i < nblocks; i++) if (ev_a[i]) cudaEventDestroy(ev_a[i]); delete[] ev_a; }
-  if (ev_b) { for (int j = 0; j < npanels; j++) if (ev_b[j]) cudaEventDestroy(ev_b[j]); delete[] ev_b; }
-  for (int c = 0; c < 4; c++) if (ev_k[c]) cudaEventDestroy(ev_k[c]);
   if (ev_start) cudaEventDestroy(ev_start);
   if (ev_tile) cudaEventDestroy(ev_tile);
+  if (ev_in) cudaEventDestroy(ev_in);
   ws_free(dC, s); ws_free(dB, s); ws_free(dA, s);
   if (sin) cudaStreamDestroy(sin);
   if (sout) cudaStreamDestroy(sout);

@@ -166,6 +166,25 @@ Residency classify(const void *p);
 int ws_alloc(void **p, size_t bytes, cudaStream_t s);
 void ws_free(void *p, cudaStream_t s);
 
+// Host <-> device 2-D copies of one library call.  Pinned / registered host memory: plain cudaMemcpy2DAsync.  Pageable
+// memory (what a stock Jalla Matrix is): the library's own staging through pinned slots filled by several host threads
+// (host_stage.cu) — h2d blocks only for the host-side copy of a slot, d2h returns once the device side is queued;
+// finish() (or the destructor) returns when every d2h has reached the caller's memory.
+bool is_pageable(const void *p);
+class HostStage {
+ public:
+  HostStage();
+  ~HostStage();
+  HostStage(const HostStage &) = delete;
+  HostStage &operator=(const HostStage &) = delete;
+  int h2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows, cudaStream_t st);
+  int d2h(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows, cudaStream_t st);
+  int finish();
+ private:
+  int acquire();
+  bool locked_ = false;
+};
+
 // Brings a possibly-host matrix onto the device for the duration of one call.
 // Compact copy (ld = rows) for host data; device data is used in place.
 struct Staged {
@@ -176,8 +195,9 @@ struct Staged {
   size_t esz = 0;
   long rows = 0, cols = 0; // storage shape (column-major: rows contiguous)
   bool staged = false;
+  HostStage stage;         // pageable host memory goes through the library's pinned slots
   int open(const void *p, long rows, long cols, int ld, size_t esz, bool copy_in, cudaStream_t s);
-  int close(bool copy_out, cudaStream_t s);   // async D2H + free; caller syncs
+  int close(bool copy_out, cudaStream_t s);   // D2H + free; host memory is complete when the caller has synchronised s
 };
 
 // ---- internal device-pointer entry points -----------------------------------------

@@ -112,20 +112,16 @@ int Staged::open(const void *p, long r, long c, int ld_, size_t esz_, bool copy_
   int rc = ws_alloc(&dev, (size_t)ld * (size_t)c * esz, s);
   if (rc) return rc;
   if (copy_in)
-    JB_CUDA(cudaMemcpy2DAsync(dev, (size_t)ld * esz, host, (size_t)host_ld * esz, (size_t)r * esz, (size_t)c,
-                              cudaMemcpyHostToDevice, s));
+    if (int r2 = stage.h2d(dev, (size_t)ld * esz, host, (size_t)host_ld * esz, (size_t)r * esz, (size_t)c, s)) { ws_free(dev, s); staged = false; return r2; }
   return 0;
 }
 
 int Staged::close(bool copy_out, cudaStream_t s) {
   if (!staged) return 0;
   int rc = 0;
-  if (copy_out) {
-    cudaError_t e = cudaMemcpy2DAsync(host, (size_t)host_ld * esz, dev, (size_t)ld * esz, (size_t)rows * esz,
-                                      (size_t)cols, cudaMemcpyDeviceToHost, s);
-    if (e != cudaSuccess) { set_error(JB_ERR_CUDA, "D2H copy failed: %s", cudaGetErrorString(e)); rc = JB_ERR_CUDA; }
-  }
+  if (copy_out) rc = stage.d2h(host, (size_t)host_ld * esz, dev, (size_t)ld * esz, (size_t)rows * esz, (size_t)cols, s);
   ws_free(dev, s);
+  if (int r2 = stage.finish()) rc = rc ? rc : r2;      // pageable destination: returns when the drain thread has delivered it
   staged = false;
   return rc;
 }

@@ -252,6 +252,23 @@ def test_host_pointer_solve(gpu_host, orc, rng):
     assert fro(Bg - Bo) / fro(Bo) <= 1e3 * n * EPS["d"]
 
 
+def test_host_pointer_solve_staged(gpu_host, blas, rng):
+    """Pageable host operands of 16 MB and more go through the library's own pinned-slot staging (csrc/host_stage.cu:
+    several host threads fill / drain the slots, D2H delivered by a drain thread before the call returns): padded leading
+    dimensions whose NaN padding must survive, pivots and solution against OpenBLAS, a second call re-using the slots."""
+    n, nrhs, lda, ldb = 1800, 1200, 1803, 1801           # A 26 MB, B 17 MB
+    for rep in range(2):
+        A = rand(rng, "d", n, n, lda); B = rand(rng, "d", n, nrhs, ldb)
+        Ag, Ao, Bg, Bo = A.copy(order="F"), A.copy(order="F"), B.copy(order="F"), B.copy(order="F")
+        pg, po = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        assert gpu_host.gesv("d", 102, n, nrhs, Ag, lda, pg, Bg, ldb) == 0
+        assert blas.gesv("d", 102, n, nrhs, Ao, lda, po, Bo, ldb) == 0
+        np.testing.assert_array_equal(pg, po)
+        assert fro(Bg[:n] - Bo[:n]) / fro(Bo[:n]) <= 1e3 * n * EPS["d"]
+        assert fro(Ag[:n] - Ao[:n]) / fro(Ao[:n]) <= 50 * n * EPS["d"]
+        assert np.isnan(Ag[n:]).all() and np.isnan(Bg[n:]).all()
+
+
 @pytest.mark.parametrize("t", "dz")
 @pytest.mark.parametrize("uplo", ["L", "U"])
 def test_potrf_two_level(gpu, blas, rng, t, uplo):
