@@ -493,10 +493,12 @@ class ShardedBatchedLU:
         return tot / reps
 
 
-def _batched_lu_e2e(self, steps=2, chunk=125_000):
+def _batched_lu_e2e(self, steps=2, chunk=31_250):
     """configs[2] end to end: the systems start and end in pinned HOST memory.  The batch moves in chunks of `chunk`
     systems through three streams (H2D / jb_dgesv_batched / D2H of LU, ipiv and x), so the copies of neighbouring
-    chunks overlap the kernel; PCIe carries 2 x 8.5 GB per 10^6 systems and is what bounds this figure."""
+    chunks overlap the kernel; PCIe carries 2 x 8.5 GB per 10^6 systems and is what bounds this figure.  What is not
+    overlapped is the first chunk's H2D and the last chunk's D2H, so chunks are small (256 MB: 4.7 ms each way; with
+    1 GB chunks the two ends were 38 ms of a 194 ms step)."""
     torch, lib, n = self.torch, self.lib, self.n
     nb = self.local_batch
     hA = torch.empty(nb * n * n, dtype=torch.float64, pin_memory=True); hb = torch.empty(nb * n, dtype=torch.float64, pin_memory=True)

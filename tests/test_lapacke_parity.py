@@ -269,6 +269,33 @@ def test_host_pointer_solve_staged(gpu_host, blas, rng):
         assert np.isnan(Ag[n:]).all() and np.isnan(Bg[n:]).all()
 
 
+def test_concurrent_callers_from_several_os_threads(gpu_host, blas, rng):
+    """`foreign import ccall unsafe` may enter the library from several OS threads at once (SURVEY.md §8b "Threading",
+    jalla.cabal:95 -threaded): four Python threads (ctypes releases the GIL) each run gesv on their own pageable host
+    operands — small ones on the driver's staging, large ones through the shared pinned-slot stager — and every result
+    must match OpenBLAS."""
+    import threading
+    jobs = []
+    for i, (n, nrhs) in enumerate([(1500, 1400), (300, 2), (1500, 1400), (700, 1)]):
+        A = rand(rng, "d", n, n); B = rand(rng, "d", n, nrhs)
+        jobs.append((n, nrhs, A, B))
+    out = [None] * len(jobs)
+
+    def run(i):
+        n, nrhs, A, B = jobs[i]
+        Ag, Bg, pg = A.copy(order="F"), B.copy(order="F"), np.zeros(n, np.int32)
+        info = gpu_host.gesv("d", 102, n, nrhs, Ag, n, pg, Bg, n)
+        out[i] = (info, pg, Bg)
+    th = [threading.Thread(target=run, args=(i,)) for i in range(len(jobs))]
+    for t in th: t.start()
+    for t in th: t.join()
+    for (n, nrhs, A, B), (info, pg, Bg) in zip(jobs, out):
+        Ao, Bo, po = A.copy(order="F"), B.copy(order="F"), np.zeros(n, np.int32)
+        assert info == 0 and blas.gesv("d", 102, n, nrhs, Ao, n, po, Bo, n) == 0
+        np.testing.assert_array_equal(pg, po)
+        assert fro(Bg - Bo) / fro(Bo) <= 1e3 * n * EPS["d"]
+
+
 @pytest.mark.parametrize("t", "dz")
 @pytest.mark.parametrize("uplo", ["L", "U"])
 def test_potrf_two_level(gpu, blas, rng, t, uplo):
