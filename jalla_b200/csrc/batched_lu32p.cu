@@ -479,14 +479,26 @@ template <int MODE> struct Lu32qPairs<MODE, N32> {
   static __device__ __forceinline__ void run(double (&)[N32], double &, double &, int &, int &, int &, unsigned char *) {}
 };
 
+// IOV == 3 (experiment, not the default): the results leave through a shared-memory image of the system's outputs (LU at
+// its final row positions, x, ipiv) and three bulk asynchronous copies issued by one lane.  ncu on the plain kernel
+// (profiles/ncu_lu32q_r2.txt) counts ~4.2 LSU data-pipe wavefronts per STG.64 against 2 per conflict-free STS.64, which
+// suggested the detour; measured it is SLOWER at equal occupancy (6.44 against 5.82 ms per 10^6 systems, 16 warps per SM)
+// and only level at 19 warps per SM / 96 registers (5.83) — a full-warp STS.64 costs this kernel more than the STG.64 it
+// replaces (profiles/lu32_stage_r2d.jsonl).  Needs 16-byte aligned outputs and even strides (checked by the launcher).
+constexpr int Q_STAGE_X = 1024, Q_STAGE_IPIV = 1056, Q_STAGE_DOUBLES = 1072;
+__device__ __forceinline__ void bulk_s2g(void *gdst, const void *ssrc, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+}
 template <int MODE, int WARPS, int MINB, bool REALIGN, int IOV = 0>
 __global__ void __launch_bounds__(32 * WARPS, MINB)
 lu32q_kernel(double *__restrict__ Ag, long long stride_a, int *__restrict__ ipiv_g, double *__restrict__ Bg, long long stride_b,
              double *__restrict__ Xg, long long stride_x, int *__restrict__ info_g, int *__restrict__ redo, int nsys) {
   __shared__ __align__(16) unsigned char smem_all[WARPS * Q_BYTES];
+  __shared__ __align__(128) double stage_all[IOV == 3 ? WARPS * Q_STAGE_DOUBLES : 2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char *const sm = smem_all + warp * Q_BYTES;
-  double *const xs = reinterpret_cast<double *>(sm + Q_XS);
+  double *const st = stage_all + (IOV == 3 ? warp * Q_STAGE_DOUBLES : 0);
+  double *const xs = IOV == 3 ? st + Q_STAGE_X : reinterpret_cast<double *>(sm + Q_XS);
   const int *const spos = reinterpret_cast<const int *>(sm + Q_POS);
   for (long long g0 = (long long)blockIdx.x * WARPS; g0 < nsys; g0 += (long long)gridDim.x * WARPS) {
     long long sys = g0 + warp;
@@ -508,6 +520,10 @@ lu32q_kernel(double *__restrict__ Ag, long long stride_a, int *__restrict__ ipiv
     int pos = lane, dm = 0, bad = 0;
     Lu32qPairs<MODE, 0>::run(a, bb, my_rinv, pos, dm, bad, sm);
     const unsigned badm = __ballot_sync(0xffffffffu, bad);
+    if (IOV == 3) {       // the previous system's copies have long finished reading the image; make it formal
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+    }
     if (MODE != 0) {
 #pragma unroll
       for (int k = N32 - 1; k >= 0; k--) {
@@ -517,17 +533,41 @@ lu32q_kernel(double *__restrict__ Ag, long long stride_a, int *__restrict__ ipiv
       }
     }
     if (badm == 0) {
-      if (MODE != 2) {
+      if (IOV == 3) {
+        if (MODE != 2) {
 #pragma unroll
-        for (int j = 0; j < N32; j++) { if (IOV == 1) A[pos + N32 * j] = a[j]; else __stcs(A + pos + N32 * j, a[j]); }
-        ipiv_g[sys * N32 + lane] = spos[lane] + 1;
+          for (int j = 0; j < N32; j++) st[pos + N32 * j] = a[j];
+          reinterpret_cast<int *>(st + Q_STAGE_IPIV)[lane] = spos[lane] + 1;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          if (MODE != 2) {
+            bulk_s2g(A, st, N32 * N32 * 8);
+            bulk_s2g(ipiv_g + sys * N32, st + Q_STAGE_IPIV, N32 * 4);
+          }
+          if (MODE == 1) bulk_s2g(Bg + sys * stride_b, xs, N32 * 8);
+          if (MODE == 2) bulk_s2g(Xg + sys * stride_x, xs, N32 * 8);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          if (info_g) info_g[sys] = 0;
+        }
+      } else {
+        if (MODE != 2) {
+#pragma unroll
+          for (int j = 0; j < N32; j++) { if (IOV == 1) A[pos + N32 * j] = a[j]; else __stcs(A + pos + N32 * j, a[j]); }
+          ipiv_g[sys * N32 + lane] = spos[lane] + 1;
+        }
+        if (MODE == 1) Bg[sys * stride_b + lane] = xs[lane];
+        if (MODE == 2) Xg[sys * stride_x + lane] = xs[lane];
+        if (lane == 0 && info_g) info_g[sys] = 0;
       }
-      if (MODE == 1) Bg[sys * stride_b + lane] = xs[lane];
-      if (MODE == 2) Xg[sys * stride_x + lane] = xs[lane];
-      if (lane == 0 && info_g) info_g[sys] = 0;
     } else if (lane == 0 && (REALIGN || g0 + warp < nsys)) {
       redo[1 + atomicAdd(redo, 1)] = (int)sys;
     }
+    __syncwarp();
+  }
+  if (IOV == 3) {         // the image must outlive the copies that read it
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncwarp();
   }
 }
@@ -699,6 +739,10 @@ template <int MODE, int WARPS, int MINB, bool REALIGN, int IOV = 0>
 static void launch_q(double *a, long long sa, int *ipiv, double *b, long long sb, double *x, long long sx, int *info, int *redo, int nsys, cudaStream_t s) {
   const int lim = option("lu32.ctas_per_sm");
   const long ctas = (nsys + WARPS - 1) / WARPS, cap = (long)num_sms() * (lim > 0 && lim < MINB ? lim : MINB);
+  if (IOV == 3) {        // 16 one-warp CTAs per SM need 16 x 10.6 KB of shared memory
+    auto fn = lu32q_kernel<MODE, WARPS, MINB, REALIGN, IOV>;
+    JB_ONCE_PER_DEVICE(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+  }
   lu32q_kernel<MODE, WARPS, MINB, REALIGN, IOV><<<(int)(ctas < cap ? ctas : cap), 32 * WARPS, 0, s>>>(a, sa, ipiv, b, sb, x, sx, info, redo, nsys);
   count_launch();
 }
@@ -730,6 +774,8 @@ static void launch_p(double *a, long long sa, int *ipiv, double *b, long long sb
 // variant (jb_set_option "lu32.variant", tools/time_lu32.py; 10^6 systems on B200, all bit-identical to lu32_one):
 //   30 pair-lookahead, 16 one-warp CTAs per SM   5.83 ms   <- default
 //   31 pair-lookahead, 16 warps re-aligned       6.53 ms
+//   32 / 33 pair-lookahead, outputs staged in shared memory + bulk copies, 16 / 19 warps per SM   6.44 / 5.83 ms
+//   35 pair-lookahead, 20 warps per SM at 96 registers (172 B of spills)   5.87 ms
 //    7 lane = row, shared-memory broadcast       6.14 ms      17 lane = row, shuffle broadcast        6.78 ms
 //    6 two rows per lane, shared-memory          7.05 ms      16 two rows per lane, shuffle           8.00 ms
 //  100+m / 200+m: ablations of 7 / 6 (-DJB_LU32_ABLATIONS builds only)
@@ -751,6 +797,14 @@ int lu32p_launch(int variant, double *a, long long sa, int *ipiv, double *b, lon
       case 16: launch_s<2, MODE, 1, 12, false>(a, sa, ipiv, b, sb, x, sx, info, redo, ng, s); break;
       case 17: launch_s<1, MODE, 1, 16, false>(a, sa, ipiv, b, sb, x, sx, info, redo, ng, s); break;
       case 31: launch_q<MODE, 16, 1, true>(a, sa, ipiv, b, sb, x, sx, info, redo, ng, s); break;
+      case 35: launch_q<MODE, 1, 20, false>(a, sa, ipiv, b, sb, x, sx, info, redo, ng, s); break;     // 20 warps per SM at 96 registers
+      case 32: case 33: {   // staged outputs + bulk copies; 16-byte aligned outputs and even strides, else the plain kernel
+        const bool al = (((uintptr_t)a | (uintptr_t)ipiv | (uintptr_t)b | (uintptr_t)x) & 15) == 0 && ((sa | sb | sx) & 1) == 0;
+        if (!al) launch_q<MODE, 1, 16, false>(a, sa, ipiv, b, sb, x, sx, info, redo, ng, s);
+        else if (variant == 32) launch_q<MODE, 1, 16, false, 3>(a, sa, ipiv, b, sb, x, sx, info, redo, ng, s);
+        else launch_q<MODE, 1, 20, false, 3>(a, sa, ipiv, b, sb, x, sx, info, redo, ng, s);
+        break;
+      }
       case 40: launch_b<MODE, 1, 16>(a, sa, ipiv, b, sb, x, sx, info, redo, ng, s); break;
       case 41: launch_b<MODE, 4, 4>(a, sa, ipiv, b, sb, x, sx, info, redo, ng, s); break;
       case 42: launch_b<MODE, 1, 12>(a, sa, ipiv, b, sb, x, sx, info, redo, ng, s); break;
