@@ -254,6 +254,68 @@ def test_lu32_fast_kernels_special_values_and_strides(orc, rng, variant):
         lib.jb_set_option(b"lu32.variant", -1)
 
 
+@pytest.mark.parametrize("t", "scz")
+def test_lu32g_fast_kernels_special_values_and_strides(orc, rng, t):
+    """The tuned 32x32 Float / Complex Float / Complex Double kernels (csrc/batched_lu32g.cu) against the oracle's
+    unscreened ?getf2 + ?getrs, bit for bit, on a batch that mixes generic systems with everything the fast path hands
+    to the exact routine: exact ties (integer matrices), a zero column (info > 0), NaN and Inf entries, tiny and huge
+    scales — with padded strides between systems and an odd batch, through gesv and getrf."""
+    lib.jb_init(-1)
+    n, batch = 32, 257
+    rt = "s" if t in "sc" else "d"
+    A = batch_rand(rng, t, batch, n); b = batch_rand(rng, t, batch, n, 1)
+    A[3:40] = rng.integers(-2, 3, A[3:40].shape)
+    if t in "cz":
+        A[20:40] = A[20:40] + 1j * rng.integers(-2, 3, A[20:40].shape)
+    A[41, 5, :] = 0.0                         # column 5 of system 41 is zero: info = 6
+    A[42, 7, 11] = np.nan                     # a NaN inside column 7
+    A[43, :, 3] = np.nan                      # a NaN row
+    A[44, 9, 20] = np.inf
+    tiny, huge = (1e-30, 1e30) if rt == "s" else (1e-300, 1e300)
+    A[45] *= tiny; A[46] *= huge
+    A[47, 0, :] = 0.0; A[47, 0, 0] = np.finfo(NP[rt]).smallest_subnormal
+    w = 2 if t in "cz" else 1
+    sa, sb = n * n + 16, n + 4                # padded strides between systems (in elements)
+    pad = np.nan if t == "s" else complex(np.nan, np.nan)
+    Abuf = np.full((batch, sa), pad, NP[t]); Abuf[:, :n * n] = A.reshape(batch, -1)
+    bbuf = np.full((batch, sb), pad, NP[t]); bbuf[:, :n] = b.reshape(batch, -1)
+    getf2, getrs = getattr(orc.lib, f"oracle_{t}getf2"), getattr(orc.lib, f"oracle_{t}getrs_cm")
+    getf2.restype = C.c_int; getf2.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    getrs.restype = None; getrs.argtypes = [C.c_char, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    LUo, Xo = A.copy(), b.copy()
+    pivo = np.zeros((batch, n), np.int32); infoo = np.zeros(batch, np.int32)
+    for i in range(batch):
+        infoo[i] = getf2(n, n, LUo[i].ctypes.data, n, pivo[i].ctypes.data)
+        if infoo[i] == 0:
+            getrs(b"N", n, 1, LUo[i].ctypes.data, n, pivo[i].ctypes.data, Xo[i].ctypes.data, n)
+    ok = infoo == 0
+    assert infoo[41] == 6 and ok.sum() >= batch - 3
+    real = lambda x: np.ascontiguousarray(x).view(NP[rt])
+    dA, dB = Dev(Abuf.copy()), Dev(bbuf.copy())
+    dP, dI = Dev(np.zeros((batch, n), np.int32)), Dev(np.full(batch, -7, np.int32))
+    check(getattr(lib, f"jb_{t}gesv_batched")(n, 1, dA.ptr, n, sa, dP.ptr, dB.ptr, n, sb, dI.ptr, batch), "gesv_batched"); check(lib.jb_sync(), "sync")
+    LU, X = dA.get(), dB.get()
+    np.testing.assert_array_equal(dI.get(), infoo)
+    np.testing.assert_array_equal(dP.get(), pivo)
+    assert_same_bits(real(LU[:, :n * n]), real(LUo.reshape(batch, -1)))
+    assert_same_bits(real(X[ok, :n]), real(Xo[ok].reshape(-1, n)))
+    assert np.isnan(real(LU[:, n * n:])).all() and np.isnan(real(X[:, n:])).all()          # padding untouched
+    dA2, dP2, dI2 = Dev(Abuf.copy()), Dev(np.zeros((batch, n), np.int32)), Dev(np.full(batch, -7, np.int32))
+    check(getattr(lib, f"jb_{t}getrf_batched")(n, dA2.ptr, n, sa, dP2.ptr, dI2.ptr, batch), "getrf_batched"); check(lib.jb_sync(), "sync")
+    assert_same_bits(real(dA2.get()[:, :n * n]), real(LUo.reshape(batch, -1)))
+    np.testing.assert_array_equal(dP2.get(), pivo); np.testing.assert_array_equal(dI2.get(), infoo)
+    # the fast path and the exact routine (lu32.v1 = 1) agree bit for bit on the whole batch
+    lib.jb_set_option(b"lu32.v1", 1)
+    try:
+        dA3, dB3 = Dev(Abuf.copy()), Dev(bbuf.copy())
+        dP3, dI3 = Dev(np.zeros((batch, n), np.int32)), Dev(np.full(batch, -7, np.int32))
+        check(getattr(lib, f"jb_{t}gesv_batched")(n, 1, dA3.ptr, n, sa, dP3.ptr, dB3.ptr, n, sb, dI3.ptr, batch), "gesv_batched"); check(lib.jb_sync(), "sync")
+    finally:
+        lib.jb_set_option(b"lu32.v1", -1)
+    assert_same_bits(real(dA3.get()), real(LU)); assert_same_bits(real(dB3.get()[ok]), real(X[ok]))
+    np.testing.assert_array_equal(dP3.get(), pivo); np.testing.assert_array_equal(dI3.get(), infoo)
+
+
 def test_config3_full_size_properties():
     """configs[2] at full size: 1,000,000 independent 32x32 Double systems from the synthetic
     generator.  Size-independent checks: every info is 0, every ipiv entry is in [k, n],

@@ -8,6 +8,9 @@ check(lib.jb_init(0), "init")
 lib.jb_set_stream(C.c_void_p(torch.cuda.current_stream().cuda_stream))
 HBM = 6538.9
 batch = int(os.environ.get("BATCH", 1_000_000))
+for kv in os.environ.get("JB_OPTIONS", "").split(","):      # e.g. JB_OPTIONS=lu32g.shape=24
+    if "=" in kv:
+        lib.jb_set_option(kv.split("=")[0].encode(), int(kv.split("=")[1]))
 DT = {"s": (torch.float32, 4, 1), "d": (torch.float64, 8, 1), "c": (torch.float32, 8, 2), "z": (torch.float64, 16, 2)}
 
 def ev(fn, prep, reps=3):
@@ -27,7 +30,10 @@ def fill(t, buf, rows, cols, seed, sym=0, diag=0.0):
     else:
         check(f(buf.data_ptr(), rows, rows, cols, 0, 0, seed), "fill")
 
-for t, n in (("d", 32), ("s", 32), ("z", 32), ("c", 32), ("d", 16), ("d", 24)):
+CASES = (("d", 32), ("s", 32), ("z", 32), ("c", 32), ("d", 16), ("d", 24))
+if os.environ.get("CASES"):              # e.g. CASES=s32,z32,c32
+    CASES = tuple((c[0], int(c[1:])) for c in os.environ["CASES"].split(","))
+for t, n in CASES:
     tdt, esz, w = DT[t]
     A0 = torch.empty(batch * n * n * w, dtype=tdt, device="cuda"); b0 = torch.empty(batch * n * w, dtype=tdt, device="cuda")
     A, b = torch.empty_like(A0), torch.empty_like(b0)
