@@ -770,12 +770,17 @@ static void launch_p(double *a, long long sa, int *ipiv, double *b, long long sb
   count_launch();
 }
 
+template <int MODE>
+void lu32d_run(int shape, double *a, long long sa, int *ipiv, double *b, long long sb, double *x, long long sx, int *info, int *redo,
+               int nsys, cudaStream_t s);      // batched_lu32d.cu: trailing updates on the FP64 tensor pipe
+
 // Handles the leading *done systems of the batch (a multiple of the launch granule); the caller runs the rest.
 // variant (jb_set_option "lu32.variant", tools/time_lu32.py; 10^6 systems on B200, all bit-identical to lu32_one):
 //   30 pair-lookahead, 16 one-warp CTAs per SM   5.83 ms   <- default
 //   31 pair-lookahead, 16 warps re-aligned       6.53 ms
 //   32 / 33 pair-lookahead, outputs staged in shared memory + bulk copies, 16 / 19 warps per SM   6.44 / 5.83 ms
 //   35 pair-lookahead, 20 warps per SM at 96 registers (172 B of spills)   5.87 ms
+//   50 / 51 trailing updates on the FP64 tensor pipe (batched_lu32d.cu), 16 / 12 warps per SM   7.19 / 7.47 ms
 //    7 lane = row, shared-memory broadcast       6.14 ms      17 lane = row, shuffle broadcast        6.78 ms
 //    6 two rows per lane, shared-memory          7.05 ms      16 two rows per lane, shuffle           8.00 ms
 //  100+m / 200+m: ablations of 7 / 6 (-DJB_LU32_ABLATIONS builds only)
@@ -797,6 +802,8 @@ int lu32p_launch(int variant, double *a, long long sa, int *ipiv, double *b, lon
       case 16: launch_s<2, MODE, 1, 12, false>(a, sa, ipiv, b, sb, x, sx, info, redo, ng, s); break;
       case 17: launch_s<1, MODE, 1, 16, false>(a, sa, ipiv, b, sb, x, sx, info, redo, ng, s); break;
       case 31: launch_q<MODE, 16, 1, true>(a, sa, ipiv, b, sb, x, sx, info, redo, ng, s); break;
+      case 50: lu32d_run<MODE>(16, a, sa, ipiv, b, sb, x, sx, info, redo, ng, s); break;
+      case 51: lu32d_run<MODE>(12, a, sa, ipiv, b, sb, x, sx, info, redo, ng, s); break;
       case 35: launch_q<MODE, 1, 20, false>(a, sa, ipiv, b, sb, x, sx, info, redo, ng, s); break;     // 20 warps per SM at 96 registers
       case 32: case 33: {   // staged outputs + bulk copies; 16-byte aligned outputs and even strides, else the plain kernel
         const bool al = (((uintptr_t)a | (uintptr_t)ipiv | (uintptr_t)b | (uintptr_t)x) & 15) == 0 && ((sa | sb | sx) & 1) == 0;

@@ -197,7 +197,7 @@ def test_chol32_tuned_kernels_bit_exact(orc, rng, nrhs, t):
         assert fro(X[i] - Bo) <= 1e3 * n * EPS[t] * fro(Bo)
 
 
-@pytest.mark.parametrize("variant", [30, 31, 7, 6, 17, 16])
+@pytest.mark.parametrize("variant", [30, 31, 7, 6, 17, 16, 40, 32, 50])
 def test_lu32_fast_kernels_special_values_and_strides(orc, rng, variant):
     """Every shape of the tuned 32x32 Double kernels (jb_set_option lu32.variant) against the oracle, bit for bit, on a
     batch that mixes generic systems with everything the fast path must hand to the exact routine: exact ties (integer
