@@ -289,6 +289,18 @@ constexpr int PANEL_WIDE_THREADS = 512, PANEL_WIDE_MAX_CTAS = 32;
 template <typename T> struct alignas(16) PanelRow { T rot[NB]; T lpart[NB]; };
 template <typename T> struct alignas(2 * sizeof(T)) PanelPair { T x, y; };
 
+// a[j] <- a[j+1] - l * u[j+1] for the W registers that still hold columns (a[0] is done by the caller); a[W-1] <- 0
+template <typename T, int W>
+__device__ __forceinline__ void panel_rotate(T (&a)[NB], const T l, const PanelPair<T> *up) {
+#pragma unroll
+  for (int jj = 1; jj < W / 2; jj++) {
+    const PanelPair<T> q = up[jj];
+    a[2 * jj - 1] = Num<T>::msub(a[2 * jj], l, q.x);
+    a[2 * jj] = Num<T>::msub(a[2 * jj + 1], l, q.y);
+  }
+  a[W - 1] = Num<T>::zero();
+}
+
 template <typename T, int MAXT, bool MULTI, int RPL = PANEL_REC_PER_LANE>
 __global__ void __launch_bounds__(MAXT, 1)
 lu_panel_reg_kernel(int pm, int jb, T *__restrict__ Pg, int ldg, int *__restrict__ ipiv, int *info, int row_off,
@@ -472,13 +484,12 @@ lu_panel_reg_kernel(int pm, int jb, T *__restrict__ Pg, int ldg, int *__restrict
     if (!zero) l = Num<T>::cmul(l, rinv);
     Lm[(size_t)c * nt + tid] = l;
     a[0] = Num<T>::msub(a[1], l, u0.y);
-#pragma unroll
-    for (int jj = 1; jj < NB / 2; jj++) {
-      const Pair q = up[jj];
-      a[2 * jj - 1] = Num<T>::msub(a[2 * jj], l, q.x);
-      a[2 * jj] = Num<T>::msub(a[2 * jj + 1], l, q.y);
-    }
-    a[NB - 1] = Num<T>::zero();
+    // registers >= NB - c hold no column any more (zeros): the update covers only the width that is left, in four
+    // compile-time widths so that every register index stays static (warp-uniform branch on c)
+    if (c < 8) panel_rotate<T, NB>(a, l, up);
+    else if (c < 16) panel_rotate<T, NB - 8>(a, l, up);
+    else if (c < 24) panel_rotate<T, NB - 16>(a, l, up);
+    else panel_rotate<T, NB - 24>(a, l, up);
     JB_PROF(6);
   }
   __syncthreads();
@@ -1052,6 +1063,9 @@ static int getrf_nb32(int m, int n, T *A, int lda, int *d_ipiv, int *d_info, int
     // The columns right of the panel take its interchanges and the block-row solve in one launch; the columns left
     // of it (finished L, read by nothing later in this sweep) take all their interchanges in one pass at the end.
     const int nr = n - j0 - jb;
+    // (A fused interchange + block-row solve + rank-32 update kernel for small trailing matrices was tried in round 2d:
+    // two-warp CTAs of eight columns, L21 streamed from L2 — dgesv 512 went from 0.93 to 1.11 ms, the update loop is a
+    // chain of L2 round trips without enough warps to hide them; the two launch-bound kernels below stayed.)
     if (nr > 0) {
       const int cols_per_cta = (LASWP_THREADS / 32) * LASWP_COLS_PER_WARP;
       laswp_trsm_kernel<T><<<(nr + cols_per_cta - 1) / cols_per_cta, LASWP_THREADS, 0, s>>>(A, lda, j0 + jb, n, d_ipiv, j0, j0 + jb,
@@ -1437,8 +1451,11 @@ getrs_fused_kernel(int n, const T *__restrict__ A, int lda, const int *__restric
     for (int r = j0 + NB + tid; r < n; r += nt) {
       T acc = x[r];
       const T *Ar = A + r + (size_t)j0 * lda;
-#pragma unroll 8
-      for (int i = 0; i < NB; i++) acc = Num<T>::msub(acc, Ar[(size_t)i * lda], xb[i]);
+      T av[NB];                                   // all 32 entries of the row in flight at once: one L2 round trip
+#pragma unroll
+      for (int i = 0; i < NB; i++) av[i] = Ar[(size_t)i * lda];
+#pragma unroll
+      for (int i = 0; i < NB; i++) acc = Num<T>::msub(acc, av[i], xb[i]);
       x[r] = acc;
     }
     if (bi + 1 < nblk) stash(e0, e1);
@@ -1467,7 +1484,15 @@ getrs_fused_kernel(int n, const T *__restrict__ A, int lda, const int *__restric
     for (int r = tid; r < j0; r += nt) {
       T acc = x[r];
       const T *Ar = A + r + (size_t)j0 * lda;
-      for (int i = 0; i < jb; i++) acc = Num<T>::msub(acc, Ar[(size_t)i * lda], xb[i]);
+      if (jb == NB) {
+        T av[NB];
+#pragma unroll
+        for (int i = 0; i < NB; i++) av[i] = Ar[(size_t)i * lda];
+#pragma unroll
+        for (int i = 0; i < NB; i++) acc = Num<T>::msub(acc, av[i], xb[i]);
+      } else {
+        for (int i = 0; i < jb; i++) acc = Num<T>::msub(acc, Ar[(size_t)i * lda], xb[i]);
+      }
       x[r] = acc;
     }
     if (bi > 0) stash(e0, e1);
