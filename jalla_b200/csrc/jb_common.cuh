@@ -219,6 +219,7 @@ int zgemm_dmma_try(int ta, int tb, int m, int n, int k, cdouble alpha, const cdo
                    const cdouble *B, int ldb, cdouble beta, cdouble *C, int ldc, cudaStream_t s, int tri);
 
 template <typename T> int lacpy_device(int trans, int m, int n, const T *a, int lda, T *b, int ldb, cudaStream_t s);
+template <typename T> int getrs_upper_device(int n, int nrhs, const T *A, int lda, T *B, int ldb, cudaStream_t s);   // lapack_blocked.cu
 // counts NaNs in an m x n column-major block (tri: 0 full, 'L'/'U'); result in *d_flag (device int, pre-zeroed)
 template <typename T> int nancheck_device(int tri, int m, int n, const T *a, int lda, int *d_flag, cudaStream_t s);
 

@@ -1406,7 +1406,7 @@ static int apply_row_perm(int inverse, int n, int nrhs, const int *d_ipiv, T *B,
 constexpr int GETRS_FUSED_THREADS = 512;
 template <typename T>
 __global__ void __launch_bounds__(GETRS_FUSED_THREADS)
-getrs_fused_kernel(int n, const T *__restrict__ A, int lda, const int *__restrict__ ipiv, T *__restrict__ B, int ldb) {
+getrs_fused_kernel(int n, const T *__restrict__ A, int lda, const int *__restrict__ ipiv, T *__restrict__ B, int ldb, int upper_only) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T *x = reinterpret_cast<T *>(smem_raw);
   int *piv = reinterpret_cast<int *>(x + n);
@@ -1414,7 +1414,7 @@ getrs_fused_kernel(int n, const T *__restrict__ A, int lda, const int *__restric
   __shared__ T xb[NB];
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
   T *b = B + (size_t)blockIdx.x * ldb;
-  for (int i = tid; i < n; i += nt) { x[i] = b[i]; piv[i] = ipiv[i]; }
+  for (int i = tid; i < n; i += nt) { x[i] = b[i]; piv[i] = upper_only ? i + 1 : ipiv[i]; }
   // diagonal block (r, c) of the factor at block offset j0, zero outside the matrix; two entries per thread
   auto fetch = [&](int j0, T &e0, T &e1) {
     const int r0 = tid & 31, c0 = tid >> 5, c1 = c0 + 16;
@@ -1425,7 +1425,7 @@ getrs_fused_kernel(int n, const T *__restrict__ A, int lda, const int *__restric
   T e0, e1;
   fetch(0, e0, e1);
   __syncthreads();
-  if (tid == 0)
+  if (tid == 0 && !upper_only)
     for (int k = 0; k < n; k++) {
       const int p = piv[k] - 1;
       if (p != k && p >= 0 && p < n) { const T t = x[k]; x[k] = x[p]; x[p] = t; }
@@ -1433,8 +1433,8 @@ getrs_fused_kernel(int n, const T *__restrict__ A, int lda, const int *__restric
   stash(e0, e1);
   __syncthreads();
   const int nblk = (n + NB - 1) / NB;
-  // ---- forward: L y = P b, unit diagonal
-  for (int bi = 0; bi < nblk; bi++) {
+  // ---- forward: L y = P b, unit diagonal (skipped when the caller already holds y: gesv on the augmented matrix)
+  for (int bi = 0; bi < (upper_only ? 0 : nblk); bi++) {
     const int j0 = bi * NB, jb = min(NB, n - j0);
     if (warp == 0) {
       T xl = lane < jb ? x[j0 + lane] : Num<T>::zero();
@@ -1514,7 +1514,7 @@ int getrs_device(char trans, int n, int nrhs, const T *A, int lda, const int *d_
     if (nrhs <= fused_nrhs && n <= fused_n) {
       const size_t shm = (size_t)n * (sizeof(T) + sizeof(int));
       JB_CUDA(cudaFuncSetAttribute(getrs_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-      getrs_fused_kernel<T><<<nrhs, GETRS_FUSED_THREADS, shm, s>>>(n, A, lda, d_ipiv, B, ldb);
+      getrs_fused_kernel<T><<<nrhs, GETRS_FUSED_THREADS, shm, s>>>(n, A, lda, d_ipiv, B, ldb, 0);
       count_launch();
       JB_CUDA(cudaGetLastError());
       return 0;
@@ -1530,6 +1530,28 @@ int getrs_device(char trans, int n, int nrhs, const T *A, int lda, const int *d_
   }
   return 0;
 }
+
+// U X = Y with the stored upper factor (the second half of ?getrs): what ?gesv still has to do after factorising the
+// augmented matrix [A | B], whose extra columns leave getrf as Y = inv(L) P B.
+template <typename T>
+int getrs_upper_device(int n, int nrhs, const T *A, int lda, T *B, int ldb, cudaStream_t s) {
+  if (n <= 0 || nrhs <= 0) return 0;
+  const int fused_nrhs = option("getrs.fused_max_nrhs") >= 0 ? option("getrs.fused_max_nrhs") : 16;
+  const int fused_n = option("getrs.fused_max_n") > 0 ? option("getrs.fused_max_n") : (trsv_few_pays(n, nrhs) ? 768 : 2048);
+  if (nrhs <= fused_nrhs && n <= fused_n) {
+    const size_t shm = (size_t)n * (sizeof(T) + sizeof(int));
+    JB_CUDA(cudaFuncSetAttribute(getrs_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+    getrs_fused_kernel<T><<<nrhs, GETRS_FUSED_THREADS, shm, s>>>(n, A, lda, nullptr, B, ldb, 1);
+    count_launch();
+    JB_CUDA(cudaGetLastError());
+    return 0;
+  }
+  return trsm_left_blocked<T>(0, 111, 0, n, nrhs, A, lda, B, ldb, s);
+}
+template int getrs_upper_device<float>(int, int, const float *, int, float *, int, cudaStream_t);
+template int getrs_upper_device<double>(int, int, const double *, int, double *, int, cudaStream_t);
+template int getrs_upper_device<cfloat>(int, int, const cfloat *, int, cfloat *, int, cudaStream_t);
+template int getrs_upper_device<cdouble>(int, int, const cdouble *, int, cdouble *, int, cudaStream_t);
 
 // inv(A) from the LU factors: solves A X = I with the stored factors and overwrites A.
 // (?getri forms inv(U) and solves X L = inv(U); same inverse, different operation order —
