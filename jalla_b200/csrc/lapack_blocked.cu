@@ -934,6 +934,64 @@ __global__ void perm_from_ipiv_kernel(int n, const int *__restrict__ ipiv, int *
   __syncthreads();
   if (use_smem) for (int i = threadIdx.x; i < n; i += blockDim.x) perm[i] = w[i];
 }
+// The same permutation without the n-step serial chain (931 us at n = 16384 — more than the two triangular sweeps of a
+// one-column ?getrs together): the interchanges are taken 32 at a time, each chunk composed into ONE permutation of the
+// <= 64 positions it touches (the scheme of laswp_kernel: slots 0..31 are positions q0..q0+31, slots 32..63 the pivot
+// rows outside that range, one lane replays the chain on slot indices) — chunks are independent there, so 32 warps
+// compose 64 chunks at a time — and one warp then applies the composed chunks in order to the index vector in shared
+// memory, 64 entries per step.  Single CTA of 1024 threads; w (n ints) + the tables of 64 chunks in shared memory.
+constexpr int PERM_THREADS = 1024, PERM_BATCH = 64;
+__global__ void __launch_bounds__(PERM_THREADS)
+perm_from_ipiv_chunked_kernel(int n, const int *__restrict__ ipiv, int *__restrict__ perm) {
+  extern __shared__ int sm_perm[];
+  int *const w = sm_perm;                                   // [n]
+  int *const t_rows = sm_perm + n;                          // [PERM_BATCH][64]
+  int *const t_cur = t_rows + PERM_BATCH * 64;              // [PERM_BATCH][64]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = PERM_THREADS / 32;
+  for (int i = threadIdx.x; i < n; i += PERM_THREADS) w[i] = i;
+  const int nchunk = (n + 31) / 32;
+  for (int b0 = 0; b0 < nchunk; b0 += PERM_BATCH) {
+    const int nb = min(PERM_BATCH, nchunk - b0);
+    __syncthreads();                                        // w initialised / the previous batch applied; tables free
+    for (int q = warp; q < nb; q += nwarp) {
+      const int q0 = 32 * (b0 + q), np = min(32, n - q0);
+      int p = -1 - lane, slot = lane;                       // inactive lanes: unique dummy rows, identity slots
+      if (lane < np) {
+        p = ipiv[q0 + lane] - 1;
+        if (p < 0 || p >= n) p = q0 + lane;                 // out-of-range pivot: no interchange (as the serial kernel)
+        slot = (p >= q0 && p < q0 + 32) ? p - q0 : -1;
+      }
+      const unsigned same = __match_any_sync(0xffffffffu, p);
+      if (slot < 0) slot = 32 + (__ffs(same) - 1);
+      t_rows[q * 64 + lane] = q0 + lane;
+      t_rows[q * 64 + 32 + lane] = p;
+      t_cur[q * 64 + lane] = lane;
+      t_cur[q * 64 + 32 + lane] = 32 + lane;
+      __syncwarp();
+      for (int k = 0; k < np; k++) {
+        const int bsl = __shfl_sync(0xffffffffu, slot, k);
+        if (lane == 0) { const int t = t_cur[q * 64 + k]; t_cur[q * 64 + k] = t_cur[q * 64 + bsl]; t_cur[q * 64 + bsl] = t; }
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    if (warp == 0) {
+      for (int q = 0; q < nb; q++) {
+        const int src_lo = t_cur[q * 64 + lane], src_hi = t_cur[q * 64 + 32 + lane];
+        const bool mv_lo = src_lo != lane, mv_hi = src_hi != 32 + lane;
+        int v_lo = 0, v_hi = 0;
+        if (mv_lo) v_lo = w[t_rows[q * 64 + src_lo]];
+        if (mv_hi) v_hi = w[t_rows[q * 64 + src_hi]];
+        __syncwarp();                                       // every lane has read before any lane overwrites
+        if (mv_lo) w[t_rows[q * 64 + lane]] = v_lo;
+        if (mv_hi) w[t_rows[q * 64 + 32 + lane]] = v_hi;
+        __syncwarp();
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += PERM_THREADS) perm[i] = w[i];
+}
 // out[i,:] = in[perm[i],:]  (inverse=0)   or   out[perm[i],:] = in[i,:]  (inverse=1)
 template <typename T>
 __global__ void permute_rows_kernel(int inverse, int n, int nrhs, const int *__restrict__ perm, const T *__restrict__ in,
@@ -1384,9 +1442,15 @@ static int apply_row_perm(int inverse, int n, int nrhs, const int *d_ipiv, T *B,
   // the swap chain is n dependent steps: keep it in shared memory (opt-in size) up to n = 25600 before falling back
   // to global memory, where every step is two dependent round trips
   const int perm_smem = (size_t)n * 2 * sizeof(int) <= 200 * 1024;
-  if (perm_smem)
-    JB_CUDA(cudaFuncSetAttribute(perm_from_ipiv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  perm_from_ipiv_kernel<<<1, 256, perm_smem ? (size_t)n * 2 * sizeof(int) : 0, s>>>(n, d_ipiv, perm, perm_smem);
+  const size_t chunked_smem = ((size_t)n + 2 * PERM_BATCH * 64) * sizeof(int);
+  if (n >= 256 && chunked_smem <= 200 * 1024 && option("getrs.perm_serial") <= 0) {     // n <= 43008
+    JB_CUDA(cudaFuncSetAttribute(perm_from_ipiv_chunked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    perm_from_ipiv_chunked_kernel<<<1, PERM_THREADS, chunked_smem, s>>>(n, d_ipiv, perm);
+  } else {
+    if (perm_smem)
+      JB_CUDA(cudaFuncSetAttribute(perm_from_ipiv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    perm_from_ipiv_kernel<<<1, 256, perm_smem ? (size_t)n * 2 * sizeof(int) : 0, s>>>(n, d_ipiv, perm, perm_smem);
+  }
   dim3 grid((unsigned)min((n + 255) / 256, 1024), (unsigned)min(nrhs, 4096));
   permute_rows_kernel<T><<<grid, 256, 0, s>>>(inverse, n, nrhs, perm, B, ldb, W, n);
   count_launch(2);
@@ -1510,7 +1574,11 @@ int getrs_device(char trans, int n, int nrhs, const T *A, int lda, const int *d_
     const int fused_nrhs = option("getrs.fused_max_nrhs") >= 0 ? option("getrs.fused_max_nrhs") : 16;
     // measured (tools/time_getrs_few.py, profiles/getrs_few_r2c.jsonl; ms at n = 1024 / 2048 / 4096, one right-hand side):
     // fused 0.32 / 0.80 / 5.15, bandwidth-bound sweep (trsv_few, <= 8 columns) 0.27 / 0.52 / 0.69, blocked 0.96 / 1.88 / 4.19
-    const int fused_n = option("getrs.fused_max_n") > 0 ? option("getrs.fused_max_n") : (trsv_few_pays(n, nrhs) ? 768 : 2048);
+    // one right-hand side from order 1024 on: the persistent pipelined sweep (trsv_pipe_kernel, one launch per triangle;
+    // tools/time_trsv_pipe.py: dgetrs 1024 / 2048 / 4096 / 16384 x 1 0.259 / 0.393 / 0.690 / 2.86 -> 0.234 / 0.331 / 0.602 / 2.47 ms,
+    // at 512 the two block inversions it needs cost more than the fused kernel's whole solve: 0.194 against 0.157)
+    const bool pipe1 = nrhs == 1 && n >= 1024 && trsv_few_pays(n, 1) && option("trsv.pipe") != 0;
+    const int fused_n = option("getrs.fused_max_n") > 0 ? option("getrs.fused_max_n") : (pipe1 ? 255 : (trsv_few_pays(n, nrhs) ? 768 : 2048));
     if (nrhs <= fused_nrhs && n <= fused_n) {
       const size_t shm = (size_t)n * (sizeof(T) + sizeof(int));
       JB_CUDA(cudaFuncSetAttribute(getrs_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
@@ -1537,7 +1605,8 @@ template <typename T>
 int getrs_upper_device(int n, int nrhs, const T *A, int lda, T *B, int ldb, cudaStream_t s) {
   if (n <= 0 || nrhs <= 0) return 0;
   const int fused_nrhs = option("getrs.fused_max_nrhs") >= 0 ? option("getrs.fused_max_nrhs") : 16;
-  const int fused_n = option("getrs.fused_max_n") > 0 ? option("getrs.fused_max_n") : (trsv_few_pays(n, nrhs) ? 768 : 2048);
+  const bool pipe1 = nrhs == 1 && n >= 1024 && trsv_few_pays(n, 1) && option("trsv.pipe") != 0;
+  const int fused_n = option("getrs.fused_max_n") > 0 ? option("getrs.fused_max_n") : (pipe1 ? 255 : (trsv_few_pays(n, nrhs) ? 768 : 2048));
   if (nrhs <= fused_nrhs && n <= fused_n) {
     const size_t shm = (size_t)n * (sizeof(T) + sizeof(int));
     JB_CUDA(cudaFuncSetAttribute(getrs_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));

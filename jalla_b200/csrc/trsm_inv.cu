@@ -11,6 +11,7 @@
 // X is collected in a scratch copy (a GEMM cannot run in place) and copied back once at the end.  Inverting only the small
 // diagonal blocks keeps the error of plain blocked substitution up to the conditioning of a 64 x 64 block.
 #include "jb_common.cuh"
+#include <atomic>
 
 namespace jb {
 
@@ -257,6 +258,153 @@ trsv_step_kernel(int trans, int p0, int pb, int rest0, int cnt, const T *__restr
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// One right-hand side, ONE launch per triangle (round 2d).  The step kernel above is a launch per 64 rows — 512 dependent
+// launches at n = 16384 (2.9 ms for ?getrs against 0.35 ms of memory traffic), ~0.1 ms of the 0.9 ms of dgesv 512.  Here a
+// cooperative grid is persistent over the whole sweep and every CTA owns row blocks (of 64, in sweep order: block k goes
+// to CTA k mod P): it streams its rows' entries of op(A) block by block — left-looking, so nothing but x is ever
+// exchanged — and subtracts op(A)(k, j) x_j as soon as x_j exists, then forms x_k = op(inv(A_kk)) (b_k - sum) and
+// publishes it.  x travels as FLAGGED WORDS (4 bytes of payload + a 4-byte launch tag per 8-byte relaxed store / load,
+// single-copy atomic: a reader needs no fence, it polls the words of x_j until their tags match — the scheme of the
+// cooperative LU panel), so the dependency chain per block is one L2 round trip, one 64 x 64 product with entries that
+// were loaded while waiting, and the product with the inverted diagonal block (also loaded ahead).  The grid is
+// co-resident (cooperative launch, P <= occupancy x SMs) and a CTA walks its blocks in sweep order, so every wait ends.
+constexpr int PIPE_THREADS = 256, PIPE_Q = PIPE_THREADS / NBI, PIPE_COLS = NBI / PIPE_Q;
+__device__ __forceinline__ void pipe_store(unsigned long long *p, unsigned data, unsigned tag) {
+  const unsigned long long w = ((unsigned long long)tag << 32) | data;
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+// Thread (t, h): row t of the block, columns 16h .. 16h+15 of every block column.  PIPE_DEPTH block columns of op(A) are
+// in flight per thread (a ring of register buffers with static indices: the sweep loop is unrolled by the depth), so a
+// CTA streams its strip at memory speed instead of one DRAM round trip per 64 columns (first version, depth 1, 128
+// threads: dgetrs 16384 x 1 2.47 ms).
+template <typename T>
+__global__ void __launch_bounds__(PIPE_THREADS, 1)
+trsv_pipe_kernel(int eff_lower, int trans, int n, int nblk, const T *__restrict__ A, int lda, const T *__restrict__ Dinv,
+                 T *__restrict__ B, unsigned long long *__restrict__ flagged, unsigned tag) {
+  constexpr int W = sizeof(T) / 4, PIPE_DEPTH = sizeof(T) == 16 ? 2 : 4;      // 128 registers of operands in flight per thread
+  __shared__ __align__(16) T xs[2][NBI], part[PIPE_Q][NBI], bs[NBI], xfin[NBI];
+  const int tid = threadIdx.x, t = tid & (NBI - 1), h = tid / NBI;
+  for (int k = blockIdx.x; k < nblk; k += gridDim.x) {
+    const int c = eff_lower ? k : nblk - 1 - k;
+    const int p0 = c * NBI, pb = min(NBI, n - p0);
+    const bool live = t < pb;
+    const size_t row = (size_t)p0 + (live ? t : 0);
+    // entries of op(A)(row, q0 + 16h ..) of block column cj (zero outside the matrix)
+    auto load_block = [&](int jo, T (&a)[PIPE_COLS]) {
+      const int cj = eff_lower ? jo : nblk - 1 - jo;
+      const int q0 = cj * NBI + h * PIPE_COLS, qb = n - q0;
+      if (trans == 111) {
+        const T *Ar = A + row + (size_t)q0 * lda;
+#pragma unroll
+        for (int u = 0; u < PIPE_COLS; u++) a[u] = (live && u < qb) ? Ar[(size_t)u * lda] : Num<T>::zero();
+      } else {
+        const T *Ar = A + q0 + row * lda;
+#pragma unroll
+        for (int u = 0; u < PIPE_COLS; u++) {
+          const T v = (live && u < qb) ? Ar[u] : Num<T>::zero();
+          a[u] = trans == 113 ? Num<T>::conj(v) : v;
+        }
+      }
+    };
+    T acc = Num<T>::zero();
+    T a[PIPE_DEPTH][PIPE_COLS];
+#pragma unroll
+    for (int s = 0; s < PIPE_DEPTH; s++)
+      if (s < k) load_block(s, a[s]);
+    // this block's row of the inverted diagonal block and its right-hand side, long before they are needed
+    T d[PIPE_COLS];
+    {
+      const T *Dc = Dinv + (size_t)c * NBI * NBI;
+#pragma unroll
+      for (int u = 0; u < PIPE_COLS; u++) {
+        const int jj = h * PIPE_COLS + u;
+        const T v = (trans == 111) ? Dc[t + jj * NBI] : Dc[jj + t * NBI];
+        d[u] = trans == 113 ? Num<T>::conj(v) : v;
+      }
+    }
+    const T bk = (live && h == 0) ? B[row] : Num<T>::zero();
+    for (int j0 = 0; j0 < k; j0 += PIPE_DEPTH) {
+#pragma unroll
+      for (int s = 0; s < PIPE_DEPTH; s++) {
+        const int jo = j0 + s;
+        if (jo < k) {                                   // CTA-uniform
+          // ---- x_jo: poll its flagged words
+          unsigned *const xw = reinterpret_cast<unsigned *>(xs[s & 1]);
+          const unsigned long long *const src = flagged + (size_t)jo * NBI * W;
+          for (int w = tid; w < NBI * W; w += PIPE_THREADS) {
+            unsigned long long v;
+            do { asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(src + w) : "memory"); } while ((unsigned)(v >> 32) != tag);
+            xw[w] = (unsigned)v;
+          }
+          __syncthreads();
+#pragma unroll
+          for (int u = 0; u < PIPE_COLS; u++) acc = Num<T>::add(acc, Num<T>::mul(a[s][u], xs[s & 1][h * PIPE_COLS + u]));
+          if (jo + PIPE_DEPTH < k) load_block(jo + PIPE_DEPTH, a[s]);
+        }
+      }
+    }
+    // ---- x_k = op(inv(A_kk)) (b_k - sum)
+    part[h][t] = acc;
+    __syncthreads();
+    if (h == 0) {
+      T sum = part[0][t];
+#pragma unroll
+      for (int g = 1; g < PIPE_Q; g++) sum = Num<T>::add(sum, part[g][t]);
+      bs[t] = live ? Num<T>::sub(bk, sum) : Num<T>::zero();
+    }
+    __syncthreads();
+    T ax = Num<T>::zero();
+#pragma unroll
+    for (int u = 0; u < PIPE_COLS; u++) ax = Num<T>::add(ax, Num<T>::mul(d[u], bs[h * PIPE_COLS + u]));
+    part[h][t] = ax;
+    __syncthreads();
+    if (h == 0) {
+      T x = part[0][t];
+#pragma unroll
+      for (int g = 1; g < PIPE_Q; g++) x = Num<T>::add(x, part[g][t]);
+      if (!live) x = Num<T>::zero();
+      xfin[t] = x;
+      if (live) B[row] = x;
+    }
+    __syncthreads();
+    {
+      const unsigned *const xw = reinterpret_cast<const unsigned *>(xfin);
+      unsigned long long *const dst = flagged + (size_t)k * NBI * W;
+      for (int w = tid; w < NBI * W; w += PIPE_THREADS) pipe_store(dst + w, xw[w], tag);
+    }
+    __syncthreads();          // xs / part / bs / xfin are reused by this CTA's next block
+  }
+}
+static unsigned next_pipe_tag() {
+  static std::atomic<unsigned> seq{1};
+  unsigned v = seq.fetch_add(1);
+  return v == 0 ? seq.fetch_add(1) : v;        // never the value the flag buffer is cleared to
+}
+// One right-hand side through the persistent sweep; Dinv holds the inverted diagonal blocks.  Returns 0, or an error code.
+template <typename T>
+static int trsv_pipe_run(int eff_lower, int trans, int n, int nblk, const T *A, int lda, const T *Dinv, T *B, cudaStream_t s) {
+  constexpr int W = sizeof(T) / 4;
+  unsigned long long *flagged = nullptr;
+  const size_t bytes = sizeof(unsigned long long) * (size_t)nblk * NBI * W;
+  if (int rc = ws_alloc((void **)&flagged, bytes, s)) return rc;
+  cudaError_t e = cudaMemsetAsync(flagged, 0, bytes, s);
+  int occ = 0;
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trsv_pipe_kernel<T>, PIPE_THREADS, 0);
+  if (e == cudaSuccess) {
+    if (occ < 1) occ = 1;
+    const long cap = (long)num_sms() * occ;
+    int grid = (int)(nblk < cap ? nblk : cap);
+    unsigned tag = next_pipe_tag();
+    void *args[] = {&eff_lower, &trans, &n, &nblk, &A, &lda, &Dinv, &B, &flagged, &tag};
+    e = cudaLaunchCooperativeKernel((void *)trsv_pipe_kernel<T>, dim3(grid), dim3(PIPE_THREADS), args, 0, s);
+    count_launch();
+  }
+  ws_free(flagged, s);
+  if (e != cudaSuccess) { set_error(JB_ERR_CUDA, "trsv_pipe launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return JB_ERR_CUDA; }
+  return 0;
+}
+
 // op(Tri) X = B in place, Tri = the stored triangle of A (order n), nrhs <= TRSV_MAX_NRHS.
 template <typename T>
 int trsv_few_device(int stored_lower, int trans, int unit, int n, int nrhs, const T *A, int lda, T *B, int ldb, cudaStream_t s) {
@@ -275,6 +423,12 @@ int trsv_few_device(int stored_lower, int trans, int unit, int n, int nrhs, cons
     count_launch();
   }
   const int eff_lower = (trans == 111) ? stored_lower : !stored_lower;
+  if (e == cudaSuccess && nrhs == 1 && option("trsv.pipe") != 0) {      // one right-hand side: the persistent sweep, in place
+    const int rc = trsv_pipe_run<T>(eff_lower, trans, n, nblk, A, lda, Dinv, B, s);
+    ws_free(W, s);
+    ws_free(Dinv, s);
+    return rc;
+  }
   const bool pdl = option("trsv.pdl") != 0;
   for (int bi = 0; bi < nblk && e == cudaSuccess; bi++) {
     const int c = eff_lower ? bi : nblk - 1 - bi;
