@@ -395,6 +395,8 @@ static int trsv_pipe_run(int eff_lower, int trans, int n, int nblk, const T *A, 
     if (occ < 1) occ = 1;
     const long cap = (long)num_sms() * occ;
     int grid = (int)(nblk < cap ? nblk : cap);
+    const int lim = option("trsv.pipe_ctas");              // tests: fewer CTAs than row blocks (a CTA then walks several blocks)
+    if (lim > 0 && lim < grid) grid = lim;
     unsigned tag = next_pipe_tag();
     void *args[] = {&eff_lower, &trans, &n, &nblk, &A, &lda, &Dinv, &B, &flagged, &tag};
     e = cudaLaunchCooperativeKernel((void *)trsv_pipe_kernel<T>, dim3(grid), dim3(PIPE_THREADS), args, 0, s);

@@ -81,6 +81,34 @@ def test_trsm_few_right_hand_sides(gpu, blas, rng, t, nrhs, uplo, trans, diag):
     assert np.isnan(Bg[m:]).all()
 
 
+@pytest.mark.parametrize("t", "sdcz")
+@pytest.mark.parametrize("uplo,trans", list(itertools.product((121, 122), (111, 112, 113))))
+def test_trsv_persistent_sweep_several_blocks_per_cta(gpu, blas, rng, t, uplo, trans):
+    """One right-hand side takes the persistent pipelined sweep (trsv_pipe_kernel): order 1100 = 17 x 64 + 12 with the
+    grid capped at 5 CTAs, so that every CTA walks several row blocks in sweep order, and uncapped; against OpenBLAS and
+    against the stepped sweep (trsv.pipe = 0)."""
+    from jalla_b200._lib import lib
+    m = 1100
+    A = tri_matrix(rng, t, m, m + 1)
+    B = rand(rng, t, m, 1, m + 5)
+    Bb = B.copy(order="F")
+    blas.trsm(t, 102, 141, uplo, trans, 131, m, 1, 1.0, A, m + 1, Bb, m + 5)
+    outs = []
+    for opts in ({"trsv.pipe_ctas": 5}, {}, {"trsv.pipe": 0}):
+        for k, v in opts.items():
+            lib.jb_set_option(k.encode(), v)
+        try:
+            Bg = B.copy(order="F")
+            gpu.trsm(t, 102, 141, uplo, trans, 131, m, 1, 1.0, A, m + 1, Bg, m + 5)
+        finally:
+            for k in opts:
+                lib.jb_set_option(k.encode(), -1)
+        assert fro(Bg[:m] - Bb[:m]) / fro(Bb[:m]) <= 200 * m * EPS[t]
+        assert np.isnan(Bg[m:]).all()
+        outs.append(Bg[:m].copy())
+    np.testing.assert_array_equal(outs[0], outs[1])      # the grid size does not change a single operation
+
+
 @pytest.mark.parametrize("t", "dc")
 @pytest.mark.parametrize("side,uplo,trans", list(itertools.product((141, 142), (121, 122), (111, 113))))
 def test_trsm_recursive_halving(gpu, blas, rng, t, side, uplo, trans):
