@@ -425,11 +425,9 @@ __device__ __forceinline__ void lu32q_pair(double (&a)[N32], double &bb, double 
   const int ppos0 = spos[K];
   pos = c0 ? K : (pos == K ? ppos0 : pos);
   dm = c0 ? -1 : dm;
-  if (MODE != 0) my_rinv = dsel(c0, rk0, my_rinv);
   const bool act0 = dm == 0;
-  const double t0 = __dmul_rn(a[K], h0.x);
-  a[K] = dsel(act0, t0, a[K]);
-  const double l0 = dsel(act0, t0, 0.0);
+  mul_pred(a[K], h0.x, act0);                       // l = a * (1/pivot) on the rows still in play
+  const double l0 = dsel(act0, a[K], 0.0);
   a[K + 1] = __fma_rn(-l0, h0.y, a[K + 1]);
   // ---- step K+1: select, publish {1/pivot, lambda}; both pivot lanes publish their rows with one store per column pair
   const int hk1 = (__double2hiint(a[K + 1]) & 0x7fffffff) | dm;
@@ -450,11 +448,9 @@ __device__ __forceinline__ void lu32q_pair(double (&a)[N32], double &bb, double 
   const int ppos1 = spos[K + 1];
   pos = c1 ? K + 1 : (pos == K + 1 ? ppos1 : pos);
   dm = c1 ? -1 : dm;
-  if (MODE != 0) my_rinv = dsel(c1, rk1, my_rinv);
   const bool act1 = dm == 0;
-  const double t1 = __dmul_rn(a[K + 1], h1.x);
-  a[K + 1] = dsel(act1, t1, a[K + 1]);
-  const double l1 = dsel(act1, t1, 0.0);
+  mul_pred(a[K + 1], h1.x, act1);
+  const double l1 = dsel(act1, a[K + 1], 0.0);
   const double lambda = h1.y;
 #pragma unroll
   for (int j = K + 2; j < N32; j += 2) {
@@ -520,6 +516,8 @@ lu32q_kernel(double *__restrict__ Ag, long long stride_a, int *__restrict__ ipiv
     int pos = lane, dm = 0, bad = 0;
     Lu32qPairs<MODE, 0>::run(a, bb, my_rinv, pos, dm, bad, sm);
     const unsigned badm = __ballot_sync(0xffffffffu, bad);
+    // 1 / u_kk of this lane's row: the header of the step that chose it (one load instead of two selects per step)
+    if (MODE != 0) my_rinv = reinterpret_cast<const double2 *>(sm + Q_HDR)[pos].x;
     if (IOV == 3) {       // the previous system's copies have long finished reading the image; make it formal
       if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       __syncwarp();
