@@ -240,6 +240,47 @@ def test_info_codes(gpu, orc, rng, t):
     assert gpu.getrs(t, 102, "Q", n, 2, good, n, pg, B.copy(order="F"), n) == -2
 
 
+@pytest.mark.parametrize("t", TYPES)
+@pytest.mark.parametrize("order", [102, 101])
+def test_gesv_augmented_matrix_path(gpu, orc, rng, t, order):
+    """?gesv with <= 8 right-hand sides and 128 <= n <= 2048 factorises [A | B] (the forward substitution rides in getrf's
+    launches): factors and pivots identical to the plain getrf + getrs route (gesv.augment = 0), solution against the oracle,
+    padded leading dimensions untouched, and a singular matrix returns info > 0 with the factors stored and B untouched."""
+    from jalla_b200._lib import lib
+    n, nrhs = 300, 3
+    A = rand(rng, t, n, n, n + 2); B = rand(rng, t, n, nrhs, n + 3)
+    if order == 101:
+        A = rand(rng, t, n, n, n); B = rand(rng, t, nrhs, n, nrhs)      # row-major n x nrhs stored as its transpose
+    lda, ldb = (n + 2, n + 3) if order == 102 else (n, nrhs)
+    res = []
+    for aug in (-1, 0):
+        lib.jb_set_option(b"gesv.augment", aug)
+        try:
+            Ag, Bg, pg = A.copy(order="F"), B.copy(order="F"), np.zeros(n, np.int32)
+            assert gpu.gesv(t, order, n, nrhs, Ag, lda, pg, Bg, ldb) == 0
+        finally:
+            lib.jb_set_option(b"gesv.augment", -1)
+        res.append((Ag, Bg, pg))
+    np.testing.assert_array_equal(res[0][2], res[1][2])
+    if order == 102:
+        np.testing.assert_array_equal(res[0][0][:n], res[1][0][:n])            # the same factorisation, bit for bit
+        assert np.isnan(res[0][0][n:]).all() and np.isnan(res[0][1][n:]).all()
+    Ao, Bo, po = A.copy(order="F"), B.copy(order="F"), np.zeros(n, np.int32)
+    assert orc.gesv(t, order, n, nrhs, Ao, lda, po, Bo, ldb) == 0
+    rows = slice(0, n) if order == 102 else slice(None)
+    assert fro(res[0][1][rows] - Bo[rows]) / fro(Bo[rows]) <= 1e3 * n * EPS[t]
+    # singular: column 100 zero -> info = 101, B untouched, factors as getrf leaves them
+    if order == 102:
+        As = rand(rng, t, n, n); As[:, 100] = 0
+        Ag, Bg, pg = As.copy(order="F"), rand(rng, t, n, 1), np.zeros(n, np.int32)
+        B0 = Bg.copy(order="F")
+        assert gpu.gesv(t, 102, n, 1, Ag, n, pg, Bg, n) == 101
+        np.testing.assert_array_equal(Bg, B0)
+        Af, pf = As.copy(order="F"), np.zeros(n, np.int32)
+        assert gpu.getrf(t, 102, n, n, Af, n, pf) == 101
+        np.testing.assert_array_equal(pg, pf); np.testing.assert_array_equal(Ag, Af)
+
+
 def test_host_pointer_solve(gpu_host, orc, rng):
     """Stock Jalla `Matrix` lives in pageable host memory: the link-level drop-in stages it."""
     n = 130
