@@ -340,6 +340,39 @@ def batched_cholesky(torch, lib, check, stream, hbm_gbs, batch=LU_BATCH, n=LU_N)
             "algorithmic_bytes_per_system": {"potrf": by_f, "potrs": by_s}}
 
 
+def batched_lu_other_types(torch, lib, check, stream, hbm_gbs, batch=LU_BATCH, n=LU_N):
+    """configs[2]'s call for the other element types: jb_{s,c,z}gesv_batched (getrf + getrs, nrhs = 1) on `batch` 32 x 32
+    systems (csrc/batched_lu32g.cu); algorithmic bytes = A in, b in, LU out, ipiv out, x out."""
+    out = {}
+    for t, tdt, esz, w in (("s", torch.float32, 4, 1), ("c", torch.float32, 8, 2), ("z", torch.float64, 16, 2)):
+        A0 = torch.empty(batch * n * n * w, dtype=tdt, device="cuda"); b0 = torch.empty(batch * n * w, dtype=tdt, device="cuda")
+        fill = getattr(lib, f"jb_{t}fill_uniform")
+        if t == "s":
+            check(fill(A0.data_ptr(), n, n, batch * n, 0, 0, SEED + 7, 0, 0.0), "fill"); check(fill(b0.data_ptr(), n, n, batch, 0, 0, SEED + 8, 0, 0.0), "fill")
+        else:
+            check(fill(A0.data_ptr(), n, n, batch * n, 0, 0, SEED + 7), "fill"); check(fill(b0.data_ptr(), n, n, batch, 0, 0, SEED + 8), "fill")
+        A, b = torch.empty_like(A0), torch.empty_like(b0)
+        piv = torch.empty(batch * n, dtype=torch.int32, device="cuda"); info = torch.empty(batch, dtype=torch.int32, device="cuda")
+        gesv = getattr(lib, f"jb_{t}gesv_batched")
+        ms, reps = 0.0, 3
+        for r in range(reps + 1):
+            A.copy_(A0); b.copy_(b0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            check(gesv(n, 1, A.data_ptr(), n, n * n, piv.data_ptr(), b.data_ptr(), n, n, info.data_ptr(), batch), "gesv_batched")
+            e1.record(stream); torch.cuda.synchronize()
+            if r:
+                ms += e0.elapsed_time(e1) / reps
+        assert int(info.abs().max().item()) == 0
+        by = 2 * n * n * esz + 2 * n * esz + 4 * n
+        out[f"{t}gesv_batched"] = {"ms": ms, "solves_per_s": batch / (ms * 1e-3), "algorithmic_bytes_per_system": by,
+                                   "frac_of_hbm": batch * by / ms / 1e6 / hbm_gbs}
+        del A0, b0, A, b, piv, info
+        torch.cuda.empty_cache()
+    out["workload"] = f"{batch} systems of order 32, getrf + getrs with one right-hand side, Float / Complex Float / Complex Double"
+    return out
+
+
 def cholesky_config3(torch, lib, grid, dist, n=65536, nb=1024):
     """BASELINE.json configs[3]: dpotrf + dpotrs (nrhs = 1) of an N x N SPD Double matrix, 2-D block-cyclic over the
     ranks with NCCL panel broadcasts (jalla_b200/dist_chol.py); one warm-up pass, one timed pass, residual of the solve."""
@@ -599,6 +632,7 @@ def main():
     if world == 1 and args.only == "" and not args.no_other:
         out["factorisations"] = factorisations(torch, lib, check, stream, measured_peaks()[0])
         out["batched_cholesky"] = batched_cholesky(torch, lib, check, stream, measured_peaks()[0])
+        out["batched_lu_other_types"] = batched_lu_other_types(torch, lib, check, stream, measured_peaks()[0])
     if world == 8 and args.only == "" and not args.no_other:
         gemm.close()
         del gemm
