@@ -278,12 +278,15 @@ __device__ __forceinline__ void pipe_store(unsigned long long *p, unsigned data,
 // in flight per thread (a ring of register buffers with static indices: the sweep loop is unrolled by the depth), so a
 // CTA streams its strip at memory speed instead of one DRAM round trip per 64 columns (first version, depth 1, 128
 // threads: dgetrs 16384 x 1 2.47 ms).
-template <typename T>
+// NR right-hand sides ride together (1, 2, 4 or 8 columns per launch; columns >= nrhs are zeros that nothing stores): the
+// entries of op(A) are loaded once and feed NR accumulators, x_j travels as NR x 64 flagged elements.
+template <typename T, int NR>
 __global__ void __launch_bounds__(PIPE_THREADS, 1)
 trsv_pipe_kernel(int eff_lower, int trans, int n, int nblk, const T *__restrict__ A, int lda, const T *__restrict__ Dinv,
-                 T *__restrict__ B, unsigned long long *__restrict__ flagged, unsigned tag) {
-  constexpr int W = sizeof(T) / 4, PIPE_DEPTH = sizeof(T) == 16 ? 2 : 4;      // 128 registers of operands in flight per thread
-  __shared__ __align__(16) T xs[2][NBI], part[PIPE_Q][NBI], bs[NBI], xfin[NBI];
+                 T *__restrict__ B, int ldb, int nrhs, unsigned long long *__restrict__ flagged, unsigned tag) {
+  constexpr int W = sizeof(T) / 4;
+  constexpr int PIPE_DEPTH = (sizeof(T) == 16 || NR >= 4) ? 2 : 4;      // <= 128 registers of operands in flight per thread
+  __shared__ __align__(16) T xs[2][NR][NBI], part[PIPE_Q][NR][NBI], bs[NR][NBI], xfin[NR][NBI];
   const int tid = threadIdx.x, t = tid & (NBI - 1), h = tid / NBI;
   for (int k = blockIdx.x; k < nblk; k += gridDim.x) {
     const int c = eff_lower ? k : nblk - 1 - k;
@@ -307,12 +310,14 @@ trsv_pipe_kernel(int eff_lower, int trans, int n, int nblk, const T *__restrict_
         }
       }
     };
-    T acc = Num<T>::zero();
+    T acc[NR];
+#pragma unroll
+    for (int r = 0; r < NR; r++) acc[r] = Num<T>::zero();
     T a[PIPE_DEPTH][PIPE_COLS];
 #pragma unroll
     for (int s = 0; s < PIPE_DEPTH; s++)
       if (s < k) load_block(s, a[s]);
-    // this block's row of the inverted diagonal block and its right-hand side, long before they are needed
+    // this block's row of the inverted diagonal block and its right-hand sides, long before they are needed
     T d[PIPE_COLS];
     {
       const T *Dc = Dinv + (size_t)c * NBI * NBI;
@@ -323,7 +328,9 @@ trsv_pipe_kernel(int eff_lower, int trans, int n, int nblk, const T *__restrict_
         d[u] = trans == 113 ? Num<T>::conj(v) : v;
       }
     }
-    const T bk = (live && h == 0) ? B[row] : Num<T>::zero();
+    T bk[NR];
+#pragma unroll
+    for (int r = 0; r < NR; r++) bk[r] = (live && h == 0 && r < nrhs) ? B[row + (size_t)r * ldb] : Num<T>::zero();
     for (int j0 = 0; j0 < k; j0 += PIPE_DEPTH) {
 #pragma unroll
       for (int s = 0; s < PIPE_DEPTH; s++) {
@@ -331,47 +338,61 @@ trsv_pipe_kernel(int eff_lower, int trans, int n, int nblk, const T *__restrict_
         if (jo < k) {                                   // CTA-uniform
           // ---- x_jo: poll its flagged words
           unsigned *const xw = reinterpret_cast<unsigned *>(xs[s & 1]);
-          const unsigned long long *const src = flagged + (size_t)jo * NBI * W;
-          for (int w = tid; w < NBI * W; w += PIPE_THREADS) {
+          const unsigned long long *const src = flagged + (size_t)jo * NR * NBI * W;
+          for (int w = tid; w < NR * NBI * W; w += PIPE_THREADS) {
             unsigned long long v;
             do { asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(src + w) : "memory"); } while ((unsigned)(v >> 32) != tag);
             xw[w] = (unsigned)v;
           }
           __syncthreads();
 #pragma unroll
-          for (int u = 0; u < PIPE_COLS; u++) acc = Num<T>::add(acc, Num<T>::mul(a[s][u], xs[s & 1][h * PIPE_COLS + u]));
+          for (int u = 0; u < PIPE_COLS; u++)
+#pragma unroll
+            for (int r = 0; r < NR; r++) acc[r] = Num<T>::add(acc[r], Num<T>::mul(a[s][u], xs[s & 1][r][h * PIPE_COLS + u]));
           if (jo + PIPE_DEPTH < k) load_block(jo + PIPE_DEPTH, a[s]);
         }
       }
     }
     // ---- x_k = op(inv(A_kk)) (b_k - sum)
-    part[h][t] = acc;
+#pragma unroll
+    for (int r = 0; r < NR; r++) part[h][r][t] = acc[r];
     __syncthreads();
     if (h == 0) {
-      T sum = part[0][t];
 #pragma unroll
-      for (int g = 1; g < PIPE_Q; g++) sum = Num<T>::add(sum, part[g][t]);
-      bs[t] = live ? Num<T>::sub(bk, sum) : Num<T>::zero();
+      for (int r = 0; r < NR; r++) {
+        T sum = part[0][r][t];
+#pragma unroll
+        for (int g = 1; g < PIPE_Q; g++) sum = Num<T>::add(sum, part[g][r][t]);
+        bs[r][t] = live ? Num<T>::sub(bk[r], sum) : Num<T>::zero();
+      }
     }
     __syncthreads();
-    T ax = Num<T>::zero();
 #pragma unroll
-    for (int u = 0; u < PIPE_COLS; u++) ax = Num<T>::add(ax, Num<T>::mul(d[u], bs[h * PIPE_COLS + u]));
-    part[h][t] = ax;
+    for (int r = 0; r < NR; r++) {
+      T ax = Num<T>::zero();
+#pragma unroll
+      for (int u = 0; u < PIPE_COLS; u++) ax = Num<T>::add(ax, Num<T>::mul(d[u], bs[r][h * PIPE_COLS + u]));
+      acc[r] = ax;
+    }
+#pragma unroll
+    for (int r = 0; r < NR; r++) part[h][r][t] = acc[r];      // (part was last read before the barrier above)
     __syncthreads();
     if (h == 0) {
-      T x = part[0][t];
 #pragma unroll
-      for (int g = 1; g < PIPE_Q; g++) x = Num<T>::add(x, part[g][t]);
-      if (!live) x = Num<T>::zero();
-      xfin[t] = x;
-      if (live) B[row] = x;
+      for (int r = 0; r < NR; r++) {
+        T x = part[0][r][t];
+#pragma unroll
+        for (int g = 1; g < PIPE_Q; g++) x = Num<T>::add(x, part[g][r][t]);
+        if (!live) x = Num<T>::zero();
+        xfin[r][t] = x;
+        if (live && r < nrhs) B[row + (size_t)r * ldb] = x;
+      }
     }
     __syncthreads();
     {
       const unsigned *const xw = reinterpret_cast<const unsigned *>(xfin);
-      unsigned long long *const dst = flagged + (size_t)k * NBI * W;
-      for (int w = tid; w < NBI * W; w += PIPE_THREADS) pipe_store(dst + w, xw[w], tag);
+      unsigned long long *const dst = flagged + (size_t)k * NR * NBI * W;
+      for (int w = tid; w < NR * NBI * W; w += PIPE_THREADS) pipe_store(dst + w, xw[w], tag);
     }
     __syncthreads();          // xs / part / bs / xfin are reused by this CTA's next block
   }
@@ -381,16 +402,17 @@ static unsigned next_pipe_tag() {
   unsigned v = seq.fetch_add(1);
   return v == 0 ? seq.fetch_add(1) : v;        // never the value the flag buffer is cleared to
 }
-// One right-hand side through the persistent sweep; Dinv holds the inverted diagonal blocks.  Returns 0, or an error code.
-template <typename T>
-static int trsv_pipe_run(int eff_lower, int trans, int n, int nblk, const T *A, int lda, const T *Dinv, T *B, cudaStream_t s) {
+// Up to eight right-hand sides through the persistent sweep; Dinv holds the inverted diagonal blocks.  Returns 0, an error
+// code, or -1 when this shape is not served (Complex Double beyond four columns: shared memory).
+template <typename T, int NR>
+static int trsv_pipe_launch(int eff_lower, int trans, int n, int nblk, const T *A, int lda, const T *Dinv, T *B, int ldb, int nrhs, cudaStream_t s) {
   constexpr int W = sizeof(T) / 4;
   unsigned long long *flagged = nullptr;
-  const size_t bytes = sizeof(unsigned long long) * (size_t)nblk * NBI * W;
+  const size_t bytes = sizeof(unsigned long long) * (size_t)nblk * NR * NBI * W;
   if (int rc = ws_alloc((void **)&flagged, bytes, s)) return rc;
   cudaError_t e = cudaMemsetAsync(flagged, 0, bytes, s);
   int occ = 0;
-  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trsv_pipe_kernel<T>, PIPE_THREADS, 0);
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trsv_pipe_kernel<T, NR>, PIPE_THREADS, 0);
   if (e == cudaSuccess) {
     if (occ < 1) occ = 1;
     const long cap = (long)num_sms() * occ;
@@ -398,13 +420,21 @@ static int trsv_pipe_run(int eff_lower, int trans, int n, int nblk, const T *A, 
     const int lim = option("trsv.pipe_ctas");              // tests: fewer CTAs than row blocks (a CTA then walks several blocks)
     if (lim > 0 && lim < grid) grid = lim;
     unsigned tag = next_pipe_tag();
-    void *args[] = {&eff_lower, &trans, &n, &nblk, &A, &lda, &Dinv, &B, &flagged, &tag};
-    e = cudaLaunchCooperativeKernel((void *)trsv_pipe_kernel<T>, dim3(grid), dim3(PIPE_THREADS), args, 0, s);
+    void *args[] = {&eff_lower, &trans, &n, &nblk, &A, &lda, &Dinv, &B, &ldb, &nrhs, &flagged, &tag};
+    e = cudaLaunchCooperativeKernel((void *)trsv_pipe_kernel<T, NR>, dim3(grid), dim3(PIPE_THREADS), args, 0, s);
     count_launch();
   }
   ws_free(flagged, s);
   if (e != cudaSuccess) { set_error(JB_ERR_CUDA, "trsv_pipe launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return JB_ERR_CUDA; }
   return 0;
+}
+template <typename T>
+static int trsv_pipe_run(int eff_lower, int trans, int n, int nblk, const T *A, int lda, const T *Dinv, T *B, int ldb, int nrhs, cudaStream_t s) {
+  if (nrhs == 1) return trsv_pipe_launch<T, 1>(eff_lower, trans, n, nblk, A, lda, Dinv, B, ldb, nrhs, s);
+  if (nrhs == 2) return trsv_pipe_launch<T, 2>(eff_lower, trans, n, nblk, A, lda, Dinv, B, ldb, nrhs, s);
+  if (nrhs <= 4) return trsv_pipe_launch<T, 4>(eff_lower, trans, n, nblk, A, lda, Dinv, B, ldb, nrhs, s);
+  if constexpr (sizeof(T) < 16) return trsv_pipe_launch<T, 8>(eff_lower, trans, n, nblk, A, lda, Dinv, B, ldb, nrhs, s);
+  return -1;
 }
 
 // op(Tri) X = B in place, Tri = the stored triangle of A (order n), nrhs <= TRSV_MAX_NRHS.
@@ -425,11 +455,16 @@ int trsv_few_device(int stored_lower, int trans, int unit, int n, int nrhs, cons
     count_launch();
   }
   const int eff_lower = (trans == 111) ? stored_lower : !stored_lower;
-  if (e == cudaSuccess && nrhs == 1 && option("trsv.pipe") != 0) {      // one right-hand side: the persistent sweep, in place
-    const int rc = trsv_pipe_run<T>(eff_lower, trans, n, nblk, A, lda, Dinv, B, s);
-    ws_free(W, s);
-    ws_free(Dinv, s);
-    return rc;
+  // the persistent sweep, in place (option trsv.pipe_max_nrhs: only up to that many columns; tools/time_trsv_pipe.py, dgetrs
+  // 16384 x 4 / x 8: 3.22 / 4.93 -> 2.09 / 2.82 ms, 4096 x 8: 1.03 -> 0.61 ms against the stepped sweep below)
+  const int pipe_max = option("trsv.pipe_max_nrhs") > 0 ? option("trsv.pipe_max_nrhs") : TRSV_MAX_NRHS;
+  if (e == cudaSuccess && nrhs <= pipe_max && option("trsv.pipe") != 0) {
+    const int rc = trsv_pipe_run<T>(eff_lower, trans, n, nblk, A, lda, Dinv, B, ldb, nrhs, s);
+    if (rc >= 0) {
+      ws_free(W, s);
+      ws_free(Dinv, s);
+      return rc;
+    }
   }
   const bool pdl = option("trsv.pdl") != 0;
   for (int bi = 0; bi < nblk && e == cudaSuccess; bi++) {

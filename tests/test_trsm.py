@@ -109,6 +109,35 @@ def test_trsv_persistent_sweep_several_blocks_per_cta(gpu, blas, rng, t, uplo, t
     np.testing.assert_array_equal(outs[0], outs[1])      # the grid size does not change a single operation
 
 
+@pytest.mark.parametrize("t", "sdcz")
+@pytest.mark.parametrize("nrhs", [2, 3, 5, 8])
+@pytest.mark.parametrize("uplo,trans", list(itertools.product((121, 122), (111, 113))))
+def test_trsv_persistent_sweep_several_right_hand_sides(gpu, blas, rng, t, nrhs, uplo, trans):
+    """The persistent sweep with 2, 4 or 8 columns per launch (Complex Double beyond four columns falls back to the stepped
+    sweep): order 700, grid capped at 4 CTAs and uncapped, and the stepped sweep (trsv.pipe = 0); padded leading dimensions,
+    against OpenBLAS."""
+    from jalla_b200._lib import lib
+    m = 700
+    A = tri_matrix(rng, t, m, m + 1)
+    B = rand(rng, t, m, nrhs, m + 5)
+    Bb = B.copy(order="F")
+    blas.trsm(t, 102, 141, uplo, trans, 131, m, nrhs, 1.0, A, m + 1, Bb, m + 5)
+    outs = []
+    for opts in ({"trsv.pipe_ctas": 4}, {}, {"trsv.pipe": 0}):
+        for k, v in opts.items():
+            lib.jb_set_option(k.encode(), v)
+        try:
+            Bg = B.copy(order="F")
+            gpu.trsm(t, 102, 141, uplo, trans, 131, m, nrhs, 1.0, A, m + 1, Bg, m + 5)
+        finally:
+            for k in opts:
+                lib.jb_set_option(k.encode(), -1)
+        assert fro(Bg[:m] - Bb[:m]) / fro(Bb[:m]) <= 200 * m * EPS[t]
+        assert np.isnan(Bg[m:]).all()
+        outs.append(Bg[:m].copy())
+    np.testing.assert_array_equal(outs[0], outs[1])
+
+
 @pytest.mark.parametrize("t", "dc")
 @pytest.mark.parametrize("side,uplo,trans", list(itertools.product((141, 142), (121, 122), (111, 113))))
 def test_trsm_recursive_halving(gpu, blas, rng, t, side, uplo, trans):
